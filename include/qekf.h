@@ -1,0 +1,168 @@
+/*
+ * qekf.h -- C ABI of libqekf: a B200-native (sm_100a) batched relative-pose error-state EKF.
+ *
+ * This is the drop-in boundary for the estimator core of mbrymer/quadrotor_landing
+ * (quad_state_estimation).  The reference has no FFI layer: its boundary is the public surface of
+ * the C++ class RelativePoseEKF, used by RelativePoseEKFNode through direct member access.  Every
+ * entry point below names the reference interface it replaces (paths relative to
+ * quad_state_estimation/ in the reference repository).
+ *
+ * Conventions: plain pointers and sizes only; every function returns a qekf_status (0 = ok) and
+ * never throws; quaternions are (x,y,z,w) as in the reference's 16-vector
+ * (src/quaternion_helper.cpp:88-100); the nominal state is x = [r(3) v(3) q(4) ab(3) wb(3)]
+ * (src/relative_pose_EKF.cpp:244-245) and the covariance is over (dr, dv, dtheta, dab, dwb)
+ * (src/relative_pose_EKF.cpp:484-485), 15x15, or 9x9 when est_bias = 0.
+ *
+ * A handle owns N independent filters on one GPU.  N = 1 is the reference's single estimator; the
+ * product use is N = 10^3..10^7 Monte-Carlo / parameter-sweep instances.  There is no CPU fallback:
+ * qekf_create fails with QEKF_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef QEKF_H
+#define QEKF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QEKF_MAX_TAGS 16
+
+typedef enum qekf_status {
+    QEKF_OK = 0,
+    QEKF_ERR_BAD_ARG = 1,
+    QEKF_ERR_CUDA = 2,
+    QEKF_ERR_NOT_INITIALIZED = 3,
+    QEKF_ERR_UNSUPPORTED = 4,
+    QEKF_ERR_NO_DEVICE = 5,
+    QEKF_ERR_ALLOC = 6
+} qekf_status;
+
+typedef enum qekf_precision { QEKF_FP64 = 64, QEKF_FP32 = 32 } qekf_precision;
+
+/* Parameters the reference's caller writes into public members before initialize_params()
+ * (src/relative_pose_EKF_node.cpp:53-136; declarations include/relative_pose_EKF.hpp:67-133). */
+typedef struct qekf_params {
+    double update_freq;                  /* hpp:67  */
+    double measurement_freq;             /* hpp:69  */
+    double measurement_delay;            /* hpp:70  */
+    double measurement_delay_max;        /* hpp:71  */
+    double dyn_measurement_delay_offset; /* hpp:72  */
+    double Q_a[3], Q_w[3], Q_ab[3], Q_wb[3]; /* hpp:97-100, per-step process noise diagonals */
+    double R_r[3], R_ang[3];             /* hpp:103-104 */
+    double r_cov_init, v_cov_init, ang_cov_init, ab_cov_init, wb_cov_init; /* hpp:89-93 */
+    double ab_static[3], wb_static[3];   /* hpp:55-56 */
+    double r_v_cv[3];                    /* hpp:108, camera position in vehicle frame */
+    double q_vc[4];                      /* hpp:109, x,y,z,w (node.cpp:108-110) */
+    double camera_K[9];                  /* hpp:113, row-major (node.cpp:115-117) */
+    double tag_in_view_margin;           /* hpp:119 */
+    double tag_widths[QEKF_MAX_TAGS];    /* hpp:121 */
+    double tag_positions[3 * QEKF_MAX_TAGS]; /* hpp:122, 3 per tag (node.cpp:128-136) */
+    double small_ang_tol;                /* hpp:132 */
+    double g[3];                         /* hpp:133 */
+    int32_t camera_width, camera_height; /* hpp:114-115 */
+    int32_t n_tags;                      /* hpp:118 */
+    int32_t est_bias;                    /* hpp:75 */
+    int32_t limit_measurement_freq;      /* hpp:76 */
+    int32_t corner_margin_enbl;          /* hpp:77 */
+    int32_t direct_orien_method;         /* hpp:78 */
+    int32_t multirate_ekf;               /* hpp:79 */
+    int32_t dynamic_meas_delay;          /* hpp:80 */
+    int32_t reserved;
+} qekf_params;
+
+typedef struct qekf_handle qekf_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* RelativePoseEKF::RelativePoseEKF() defaults (src/relative_pose_EKF.cpp:29-81); members the
+ * constructor leaves uninitialised take the node's defaults (node.cpp:35,64,89-93). */
+int qekf_default_params(qekf_params *p);
+
+/* Construct N filters on CUDA device `device` and run initialize_params()
+ * (src/relative_pose_EKF.cpp:87-125).  precision: QEKF_FP64 (reference arithmetic) or QEKF_FP32. */
+int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precision, qekf_handle **out);
+int qekf_destroy(qekf_handle *h);
+
+/* Overwrite parameters and re-run initialize_params() (node.cpp:53-138 then :138).  Like the
+ * reference this resets cov_pert to cov_init but keeps the nominal state. */
+int qekf_set_params(qekf_handle *h, const qekf_params *p);
+int qekf_get_params(const qekf_handle *h, qekf_params *p);
+
+/* Per-filter parameter overrides for sweeps (no reference equivalent: the reference has one
+ * filter).  values is a HOST array [dim][N]; must be called before the first run. */
+enum {
+    QEKF_PF_Q = 0,      /* dim 12: Q_a, Q_w, Q_ab, Q_wb */
+    QEKF_PF_R = 1,      /* dim 6 : R_r, R_ang */
+    QEKF_PF_R_V_CV = 2, /* dim 3 */
+    QEKF_PF_Q_VC = 3,   /* dim 4 : x,y,z,w */
+    QEKF_PF_DELAY = 4   /* dim 2 : measurement_delay, dyn_measurement_delay_offset */
+};
+int qekf_set_filter_params(qekf_handle *h, int field, const double *values);
+
+const char *qekf_last_error_string(void);
+int qekf_num_states(const qekf_handle *h);   /* RelativePoseEKF::num_states (hpp:83) */
+int64_t qekf_num_filters(const qekf_handle *h);
+
+/* All work of a handle is issued on one CUDA stream (default: a private non-blocking stream).
+ * qekf_set_stream adopts a caller stream (a cudaStream_t passed as void*). */
+int qekf_set_stream(qekf_handle *h, void *cuda_stream);
+int qekf_sync(qekf_handle *h);
+
+/* ---- the reference's per-tick estimator interface (same inputs to every filter of the handle) -- */
+
+/* IMUSubCallback (node.cpp:144-151): latch the latest IMU sample (zero-order hold). */
+int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3]);
+/* AprilTagSubCallback (node.cpp:153-176): latch detections[0] pose + header stamp, raise
+ * measurement_ready, and on the first call run initialize_state(false). */
+int qekf_set_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp);
+/* RelativePoseEKF::initialize_state(bool) (src/relative_pose_EKF.cpp:305-344). */
+int qekf_initialize_state(qekf_handle *h, int reinit_bias);
+/* RelativePoseEKF::filter_update(double) (src/relative_pose_EKF.cpp:127-303): one tick. */
+int qekf_filter_update(qekf_handle *h, double t_curr);
+
+/* ---- batch replay: filter_update iterated n_steps times inside one kernel launch -------------- */
+
+/* Explicit per-filter input streams.  Tick k (absolute index) runs at t_curr = t_start + k/update_freq.
+ * Before tick k's update, arrival m with tag_step[m] == k is delivered exactly as AprilTagSubCallback
+ * would (per filter, skipped where tag_valid[m][i] == 0), then imu[k] is latched as IMUSubCallback
+ * would.  tag_step must be strictly increasing. */
+typedef struct qekf_streams {
+    int64_t T;               /* ticks held in imu */
+    const double *imu;       /* [T][6][N]  accel xyz, gyro xyz */
+    int64_t M;               /* tag arrivals */
+    const int32_t *tag_step; /* [M] */
+    const double *tag_pose;  /* [M][7][N]  r_c_tc xyz, q_ct xyzw */
+    const double *tag_stamp; /* [M]  capture time (s), used by dynamic_meas_delay */
+    const uint8_t *tag_valid;/* [M][N] or NULL (= all valid) */
+    double t_start;
+    int32_t on_device;       /* 0: host pointers (copied in by the call); 1: device pointers */
+    int32_t reserved;
+} qekf_streams;
+
+int qekf_run(qekf_handle *h, const qekf_streams *s, int64_t k0, int64_t n_steps);
+
+/* ---- accessors (what the node reads after each tick, node.cpp:184-281) ------------------------ */
+/* All outputs are HOST arrays in [component][count] layout (component-major). */
+int qekf_get_state(qekf_handle *h, int64_t first, int64_t count, double *x16);   /* r_nom v_nom q_nom ab_nom wb_nom */
+int qekf_get_cov(qekf_handle *h, int64_t first, int64_t count, double *P);       /* cov_pert, [n*n][count], symmetric */
+/* aux: accel_rel(3) r_t_vt_obs(3) q_tv_obs(4,xyzw) measurement_delay_curr(1) -> [11][count] */
+int qekf_get_aux(qekf_handle *h, int64_t first, int64_t count, double *aux11);
+/* flags: state_initialized, measurement_ready, performed_correction, filter_active,
+ *        upds_since_correction, history length -> [6][count] */
+int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6);
+/* Overwrite nominal state and covariance (marks the filters initialised; history <- this entry).
+ * x16 [16][count], P [n*n][count] (upper triangle is used).  Checkpoint/resume and step tests. */
+int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x16, const double *P);
+
+/* ---- stateless step functions over a batch (private methods of the reference class) ----------- */
+/* prediction_step (src/relative_pose_EKF.cpp:346-415) applied to the handle's current state with
+ * per-filter inputs u [6][N] (host).  Writes accel_rel. */
+int qekf_prediction_step(qekf_handle *h, const double *u);
+/* correction_step (src/relative_pose_EKF.cpp:417-502) with per-filter tag pose [7][N] (host). */
+int qekf_correction_step(qekf_handle *h, const double *tag_pose);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QEKF_H */

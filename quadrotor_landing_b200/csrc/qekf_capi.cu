@@ -1,0 +1,634 @@
+// qekf_capi.cu -- host side of libqekf: handle, parameter derivation, launches, and the C ABI declared
+// in include/qekf.h.  Host code is C++ over the CUDA runtime; nothing here falls back to the CPU.
+#include "../../include/qekf.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ekf_kernels.cuh"
+#include "ekf_params.hpp"
+
+using namespace qekf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(QEKF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+constexpr int BLOCK = 32;   // one warp per CTA: no intra-CTA synchronisation is ever needed
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct qekf_handle {
+    qekf_params p;
+    int precision = QEKF_FP64;
+    int device = 0;
+    int64_t n = 0, ld = 0;
+    int nstates = 15, np = 120;
+    size_t tsize = 8;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void *x = nullptr, *P = nullptr, *aux = nullptr;
+    double *pend = nullptr;
+    int32_t *flags = nullptr, *upds = nullptr;
+    // per-tick interface staging
+    double *d_tick = nullptr;        // [6 imu][8 tag]
+    double *h_tick = nullptr;        // pinned mirror
+    int32_t *d_no_steps = nullptr;
+    double imu_latched[6] = { 0, 0, 0, 0, 0, 0 };
+    // cached device copies of host streams (qekf_run with on_device = 0)
+    void *d_in = nullptr;
+    size_t d_in_bytes = 0;
+    // launch bookkeeping
+    int64_t launches = 0;
+};
+
+namespace {
+
+template <typename T> DeviceState<T> dstate(const qekf_handle *h)
+{
+    DeviceState<T> s;
+    s.x = (T *)h->x; s.P = (T *)h->P; s.aux = (T *)h->aux; s.pend = h->pend;
+    s.flags = h->flags; s.upds = h->upds; s.ld = h->ld; s.n = h->n;
+    return s;
+}
+
+size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize; }
+unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
+
+template <typename K> int prep_kernel(K kernel, size_t smem)
+{
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    return QEKF_OK;
+}
+
+// dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision
+#define QEKF_DISPATCH(h, CALL)                                                             \
+    do {                                                                                   \
+        const bool b__ = (h)->p.est_bias != 0, d__ = (h)->p.direct_orien_method != 0;      \
+        if ((h)->precision == QEKF_FP64) {                                                 \
+            if (b__ && d__) { CALL(double, true, true); }                                  \
+            else if (b__) { CALL(double, true, false); }                                   \
+            else if (d__) { CALL(double, false, true); }                                   \
+            else { CALL(double, false, false); }                                           \
+        } else {                                                                           \
+            if (b__ && d__) { CALL(float, true, true); }                                   \
+            else if (b__) { CALL(float, true, false); }                                    \
+            else if (d__) { CALL(float, false, true); }                                    \
+            else { CALL(float, false, false); }                                            \
+        }                                                                                  \
+    } while (0)
+
+int free_state(qekf_handle *h)
+{
+    cudaFree(h->x); cudaFree(h->P); cudaFree(h->aux); cudaFree(h->pend);
+    cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
+    if (h->h_tick) cudaFreeHost(h->h_tick);
+    h->x = h->P = h->aux = nullptr; h->pend = nullptr; h->flags = h->upds = nullptr;
+    h->d_tick = nullptr; h->h_tick = nullptr; h->d_in = nullptr; h->d_in_bytes = 0;
+    return QEKF_OK;
+}
+
+int alloc_state(qekf_handle *h)
+{
+    h->nstates = h->p.est_bias ? 15 : 9;
+    h->np = h->nstates * (h->nstates + 1) / 2;
+    h->tsize = (h->precision == QEKF_FP64) ? 8 : 4;
+    const size_t ld = (size_t)h->ld;
+    CUDA_TRY(cudaMalloc(&h->x, 16 * ld * h->tsize));
+    CUDA_TRY(cudaMalloc(&h->P, (size_t)h->np * ld * h->tsize));
+    CUDA_TRY(cudaMalloc(&h->aux, AUX_DIM * ld * h->tsize));
+    CUDA_TRY(cudaMalloc(&h->pend, PEND_DIM * ld * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->flags, ld * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->upds, ld * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_tick, 16 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&h->h_tick, 16 * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(h->x, 0, 16 * ld * h->tsize, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->P, 0, (size_t)h->np * ld * h->tsize, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->aux, 0, AUX_DIM * ld * h->tsize, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->pend, 0, PEND_DIM * ld * sizeof(double), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->flags, 0, ld * sizeof(int32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->upds, 0, ld * sizeof(int32_t), h->stream));
+    return QEKF_OK;
+}
+
+// q_nom = identity, q_tv_obs = identity, cov_pert = cov_init   (constructor, cpp:21,26 and :114)
+template <typename T> __global__ void reset_kernel(DeviceState<T> st, Consts<T> c, int nstates, int reset_nominal)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    if (reset_nominal) {
+        st.x[9 * st.ld + i] = T(1);
+        st.aux[9 * st.ld + i] = T(1);
+    }
+    int e = 0;
+    for (int a = 0; a < nstates; ++a)
+        for (int b = a; b < nstates; ++b, ++e) st.P[e * st.ld + i] = (a == b) ? c.cov_init[a / 3] : T(0);
+}
+
+int reset_cov(qekf_handle *h, bool reset_nominal)
+{
+    const unsigned g = (unsigned)((h->n + 127) / 128);
+    if (h->precision == QEKF_FP64)
+        reset_kernel<double><<<g, 128, 0, h->stream>>>(dstate<double>(h), make_consts<double>(h->p), h->nstates, reset_nominal);
+    else
+        reset_kernel<float><<<g, 128, 0, h->stream>>>(dstate<float>(h), make_consts<float>(h->p), h->nstates, reset_nominal);
+    CUDA_TRY(cudaGetLastError());
+    return QEKF_OK;
+}
+
+int check_params(const qekf_params *p)
+{
+    if (!p) return fail(QEKF_ERR_BAD_ARG, "params is NULL");
+    if (!(p->update_freq > 0) || !(p->measurement_freq > 0)) return fail(QEKF_ERR_BAD_ARG, "rates must be positive");
+    if (p->n_tags < 0 || p->n_tags > QEKF_MAX_TAGS) return fail(QEKF_ERR_BAD_ARG, "n_tags out of range");
+    if (p->multirate_ekf) return fail(QEKF_ERR_UNSUPPORTED, "multirate_ekf is not built yet");
+    return QEKF_OK;
+}
+
+template <typename T, bool BIAS, bool DIRECT>
+int launch_run(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0)
+{
+    RunArgs<T> a;
+    a.st = dstate<T>(h);
+    a.in = in;
+    a.c = make_consts<T>(h->p);
+    a.k0 = k0; a.n_steps = n_steps; a.m0 = m0;
+    auto kern = run_kernel<T, BIAS, DIRECT, BLOCK>;
+    int rc = prep_kernel(kern, smem_bytes(h));
+    if (rc) return rc;
+    kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return QEKF_OK;
+}
+
+int run_dispatch(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0)
+{
+#define CALL_RUN(T, B, D) return launch_run<T, B, D>(h, in, k0, n_steps, m0)
+    QEKF_DISPATCH(h, CALL_RUN);
+#undef CALL_RUN
+    return QEKF_OK;
+}
+
+// copy a [rows][count] slab out of a [rows][ld] device array of element size tsize into doubles
+int fetch_rows(qekf_handle *h, const void *dev, int rows, int64_t first, int64_t count, double *out)
+{
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->precision == QEKF_FP64) {
+        CUDA_TRY(cudaMemcpy2D(out, (size_t)count * 8, (const char *)dev + (size_t)first * 8, (size_t)h->ld * 8,
+                              (size_t)count * 8, (size_t)rows, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<float> tmp((size_t)rows * (size_t)count);
+        CUDA_TRY(cudaMemcpy2D(tmp.data(), (size_t)count * 4, (const char *)dev + (size_t)first * 4, (size_t)h->ld * 4,
+                              (size_t)count * 4, (size_t)rows, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < tmp.size(); ++k) out[k] = (double)tmp[k];
+    }
+    return QEKF_OK;
+}
+
+int store_rows(qekf_handle *h, void *dev, int rows, int64_t first, int64_t count, const double *in)
+{
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->precision == QEKF_FP64) {
+        CUDA_TRY(cudaMemcpy2D((char *)dev + (size_t)first * 8, (size_t)h->ld * 8, in, (size_t)count * 8,
+                              (size_t)count * 8, (size_t)rows, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> tmp((size_t)rows * (size_t)count);
+        for (size_t k = 0; k < tmp.size(); ++k) tmp[k] = (float)in[k];
+        CUDA_TRY(cudaMemcpy2D((char *)dev + (size_t)first * 4, (size_t)h->ld * 4, tmp.data(), (size_t)count * 4,
+                              (size_t)count * 4, (size_t)rows, cudaMemcpyHostToDevice));
+    }
+    return QEKF_OK;
+}
+
+bool range_ok(const qekf_handle *h, int64_t first, int64_t count)
+{
+    return h && first >= 0 && count >= 0 && first + count <= h->n;
+}
+
+int ensure_in(qekf_handle *h, size_t bytes)
+{
+    if (bytes <= h->d_in_bytes) return QEKF_OK;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_in);
+    h->d_in = nullptr; h->d_in_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_in, bytes));
+    h->d_in_bytes = bytes;
+    return QEKF_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *qekf_last_error_string(void) { return g_err.c_str(); }
+
+int qekf_default_params(qekf_params *p)
+{
+    if (!p) return fail(QEKF_ERR_BAD_ARG, "params is NULL");
+    std::memset(p, 0, sizeof *p);
+    p->update_freq = 100;                 // cpp:29
+    p->measurement_freq = 10;             // cpp:30
+    p->measurement_delay = 0.010;         // cpp:31
+    p->measurement_delay_max = 0.200;     // cpp:32
+    p->dyn_measurement_delay_offset = 0;  // node.cpp:35
+    for (int i = 0; i < 3; ++i) {         // cpp:43-46
+        p->Q_a[i] = 0.005; p->Q_w[i] = 0.0005; p->Q_ab[i] = 5e-5; p->Q_wb[i] = 5e-6;
+    }
+    p->R_r[0] = 0.005; p->R_r[1] = 0.005; p->R_r[2] = 0.015;        // cpp:50
+    p->R_ang[0] = 0.0025; p->R_ang[1] = 0.0025; p->R_ang[2] = 0.025; // cpp:51
+    p->r_cov_init = 0.1; p->v_cov_init = 0.1; p->ang_cov_init = 0.15; // node.cpp:89-93
+    p->ab_cov_init = 0.5; p->wb_cov_init = 0.1;
+    p->r_v_cv[2] = -0.073;                // cpp:55
+    p->q_vc[0] = 0.70711; p->q_vc[1] = -0.70711;  // cpp:56 (w,x,y,z ctor) == node.cpp:109 (x,y,z,w array)
+    p->camera_K[0] = 241.4268; p->camera_K[2] = 376.5;   // cpp:59-61
+    p->camera_K[4] = 241.4268; p->camera_K[5] = 240.5; p->camera_K[8] = 1;
+    p->camera_width = 752; p->camera_height = 480;       // cpp:62-63
+    p->n_tags = 1; p->tag_in_view_margin = 0.02;         // cpp:66-67
+    p->tag_widths[0] = 0.8;                              // cpp:69
+    p->small_ang_tol = 1e-10; p->g[2] = -9.8;            // cpp:80-81
+    p->est_bias = 1; p->limit_measurement_freq = 0; p->corner_margin_enbl = 1;   // cpp:34-36
+    p->direct_orien_method = 0; p->multirate_ekf = 0; p->dynamic_meas_delay = 0; // cpp:37-38, node.cpp:64
+    return QEKF_OK;
+}
+
+int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precision, qekf_handle **out)
+{
+    if (!out) return fail(QEKF_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n_filters <= 0) return fail(QEKF_ERR_BAD_ARG, "n_filters must be positive");
+    if (precision != QEKF_FP64 && precision != QEKF_FP32) return fail(QEKF_ERR_BAD_ARG, "precision must be 64 or 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(QEKF_ERR_NO_DEVICE, "no CUDA device available (libqekf has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(QEKF_ERR_BAD_ARG, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(QEKF_ERR_NO_DEVICE, "libqekf is built for sm_100a (B200) only");
+    qekf_handle *h = new (std::nothrow) qekf_handle;
+    if (!h) return fail(QEKF_ERR_ALLOC, "out of host memory");
+    h->p = *p; h->precision = precision; h->device = device;
+    h->n = n_filters; h->ld = (n_filters + 31) / 32 * 32;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(QEKF_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    h->own_stream = true;
+    rc = alloc_state(h);
+    if (!rc) rc = reset_cov(h, true);
+    if (rc) { free_state(h); cudaStreamDestroy(h->stream); delete h; return rc; }
+    *out = h;
+    return QEKF_OK;
+}
+
+int qekf_destroy(qekf_handle *h)
+{
+    if (!h) return QEKF_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_state(h);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QEKF_OK;
+}
+
+int qekf_set_params(qekf_handle *h, const qekf_params *p)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    int rc = check_params(p);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const bool shape_change = (p->est_bias != 0) != (h->p.est_bias != 0);
+    h->p = *p;
+    if (shape_change) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        free_state(h);
+        rc = alloc_state(h);
+        if (rc) return rc;
+        return reset_cov(h, true);
+    }
+    return reset_cov(h, false);   // initialize_params: cov_pert = cov_init (cpp:114)
+}
+
+int qekf_get_params(const qekf_handle *h, qekf_params *p)
+{
+    if (!h || !p) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    *p = h->p;
+    return QEKF_OK;
+}
+
+int qekf_set_filter_params(qekf_handle *h, int field, const double *values)
+{
+    (void)field; (void)values;
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    return fail(QEKF_ERR_UNSUPPORTED, "per-filter parameter overrides are not built yet");
+}
+
+int qekf_num_states(const qekf_handle *h) { return h ? h->nstates : 0; }
+int64_t qekf_num_filters(const qekf_handle *h) { return h ? h->n : 0; }
+
+int qekf_set_stream(qekf_handle *h, void *cuda_stream)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return QEKF_OK;
+}
+
+int qekf_sync(qekf_handle *h)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QEKF_OK;
+}
+
+// ---- per-tick estimator interface ----------------------------------------------------------------
+
+int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3])
+{
+    if (!h || !accel || !gyro) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    for (int i = 0; i < 3; ++i) { h->imu_latched[i] = accel[i]; h->imu_latched[3 + i] = gyro[i]; }
+    return QEKF_OK;
+}
+
+static int deliver(qekf_handle *h, int force_init, int reinit_bias)
+{
+#define CALL_DELIVER(T, B, D)                                                                          \
+    do {                                                                                               \
+        auto kern = deliver_tag_kernel<T, B, BLOCK>;                                                   \
+        int rc__ = prep_kernel(kern, smem_bytes(h));                                                   \
+        if (rc__) return rc__;                                                                         \
+        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p),      \
+                                                              h->d_tick + 8, force_init, reinit_bias); \
+    } while (0)
+    QEKF_DISPATCH(h, CALL_DELIVER);
+#undef CALL_DELIVER
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return QEKF_OK;
+}
+
+int qekf_set_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp)
+{
+    if (!h || !pos || !quat_xyzw) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // the pinned staging buffer is reused
+    for (int i = 0; i < 3; ++i) h->h_tick[8 + i] = pos[i];
+    for (int i = 0; i < 4; ++i) h->h_tick[11 + i] = quat_xyzw[i];
+    h->h_tick[15] = stamp;
+    CUDA_TRY(cudaMemcpyAsync(h->d_tick + 8, h->h_tick + 8, 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return deliver(h, 0, 0);
+}
+
+int qekf_initialize_state(qekf_handle *h, int reinit_bias)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return deliver(h, 1, reinit_bias);
+}
+
+int qekf_filter_update(qekf_handle *h, double t_curr)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 6; ++i) h->h_tick[i] = h->imu_latched[i];
+    CUDA_TRY(cudaMemcpyAsync(h->d_tick, h->h_tick, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    StreamView in;
+    std::memset(&in, 0, sizeof in);
+    in.imu = h->d_tick; in.cs = 1; in.is = 0; in.M = 0;
+    in.tag_pose = h->d_tick + 8;      // never read: M = 0 and the latched pose lives in st.pend
+    in.t_start = t_curr; in.update_freq = h->p.update_freq;
+    return run_dispatch(h, in, 0, 1, 0);
+}
+
+// ---- batch replay ----------------------------------------------------------------------------------
+
+int qekf_run(qekf_handle *h, const qekf_streams *s, int64_t k0, int64_t n_steps)
+{
+    if (!h || !s) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (n_steps == 0) return QEKF_OK;
+    if (k0 < 0 || n_steps < 0 || k0 + n_steps > s->T) return fail(QEKF_ERR_BAD_ARG, "tick range outside the stream");
+    if (!s->imu) return fail(QEKF_ERR_BAD_ARG, "imu stream is NULL");
+    if (s->M < 0 || (s->M > 0 && (!s->tag_step || !s->tag_pose || !s->tag_stamp)))
+        return fail(QEKF_ERR_BAD_ARG, "tag streams are NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int64_t N = h->n, M = s->M, T = s->T;
+
+    // arrivals must be strictly increasing; the first one at or after k0 is where this launch starts
+    std::vector<int32_t> steps_host;
+    const int32_t *steps = s->tag_step;
+    if (s->on_device && M > 0) {
+        steps_host.resize((size_t)M);
+        CUDA_TRY(cudaMemcpy(steps_host.data(), s->tag_step, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        steps = steps_host.data();
+    }
+    int32_t m0 = 0;
+    for (int64_t m = 0; m < M; ++m) {
+        if (m > 0 && steps[m] <= steps[m - 1]) return fail(QEKF_ERR_BAD_ARG, "tag_step must be strictly increasing");
+        if (steps[m] < k0) m0 = (int32_t)(m + 1);
+    }
+
+    StreamView in;
+    std::memset(&in, 0, sizeof in);
+    in.cs = N; in.is = 1; in.M = M; in.vs = N;
+    in.t_start = s->t_start; in.update_freq = h->p.update_freq;
+    if (s->on_device) {
+        in.imu = s->imu; in.tag_step = s->tag_step; in.tag_pose = s->tag_pose;
+        in.tag_stamp = s->tag_stamp; in.tag_valid = s->tag_valid;
+    } else {
+        // host streams: stage the ticks of this call (and every arrival) into one device slab
+        const size_t imu_b = (size_t)n_steps * 6 * (size_t)N * 8;
+        const size_t pose_b = (size_t)M * 7 * (size_t)N * 8;
+        const size_t stamp_b = (size_t)M * 8, step_b = (size_t)M * 4;
+        const size_t valid_b = s->tag_valid ? (size_t)M * (size_t)N : 0;
+        size_t o_imu = 0, o_pose = align_up(o_imu + imu_b, 256), o_stamp = align_up(o_pose + pose_b, 256);
+        size_t o_step = align_up(o_stamp + stamp_b, 256), o_valid = align_up(o_step + step_b, 256);
+        size_t total = align_up(o_valid + valid_b, 256);
+        int rc = ensure_in(h, total);
+        if (rc) return rc;
+        char *d = (char *)h->d_in;
+        CUDA_TRY(cudaMemcpyAsync(d + o_imu, s->imu + (size_t)k0 * 6 * (size_t)N, imu_b, cudaMemcpyHostToDevice, h->stream));
+        if (M > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d + o_pose, s->tag_pose, pose_b, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(d + o_stamp, s->tag_stamp, stamp_b, cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(d + o_step, s->tag_step, step_b, cudaMemcpyHostToDevice, h->stream));
+            if (valid_b) CUDA_TRY(cudaMemcpyAsync(d + o_valid, s->tag_valid, valid_b, cudaMemcpyHostToDevice, h->stream));
+        }
+        // the staged imu slab starts at tick k0: bias the base pointer so absolute tick indices work
+        in.imu = (const double *)(d + o_imu) - (size_t)k0 * 6 * (size_t)N;
+        in.tag_pose = (const double *)(d + o_pose);
+        in.tag_stamp = (const double *)(d + o_stamp);
+        in.tag_step = (const int32_t *)(d + o_step);
+        in.tag_valid = valid_b ? (const uint8_t *)(d + o_valid) : nullptr;
+    }
+    (void)T;
+    return run_dispatch(h, in, k0, n_steps, m0);
+}
+
+// ---- accessors ---------------------------------------------------------------------------------------
+
+int qekf_get_state(qekf_handle *h, int64_t first, int64_t count, double *x16)
+{
+    if (!range_ok(h, first, count) || !x16) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return fetch_rows(h, h->x, 16, first, count, x16);
+}
+
+int qekf_get_cov(qekf_handle *h, int64_t first, int64_t count, double *P)
+{
+    if (!range_ok(h, first, count) || !P) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<double> packed((size_t)h->np * (size_t)count);
+    int rc = fetch_rows(h, h->P, h->np, first, count, packed.data());
+    if (rc) return rc;
+    const int n = h->nstates;
+    int e = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a; b < n; ++b, ++e) {
+            const double *src = packed.data() + (size_t)e * (size_t)count;
+            std::memcpy(P + ((size_t)a * n + b) * (size_t)count, src, (size_t)count * 8);
+            if (a != b) std::memcpy(P + ((size_t)b * n + a) * (size_t)count, src, (size_t)count * 8);
+        }
+    return QEKF_OK;
+}
+
+int qekf_get_aux(qekf_handle *h, int64_t first, int64_t count, double *aux11)
+{
+    if (!range_ok(h, first, count) || !aux11) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return fetch_rows(h, h->aux, AUX_DIM, first, count, aux11);
+}
+
+int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6)
+{
+    if (!range_ok(h, first, count) || !flags6) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<int32_t> fl((size_t)count), up((size_t)count);
+    CUDA_TRY(cudaMemcpy(fl.data(), h->flags + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(up.data(), h->upds + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < count; ++i) {
+        const int32_t f = fl[(size_t)i];
+        flags6[0 * count + i] = (f & FLAG_INIT) ? 1 : 0;
+        flags6[1 * count + i] = (f & FLAG_READY) ? 1 : 0;
+        flags6[2 * count + i] = (f & FLAG_CORRECTED) ? 1 : 0;
+        flags6[3 * count + i] = (f & FLAG_ACTIVE) ? 1 : 0;
+        flags6[4 * count + i] = up[(size_t)i];
+        flags6[5 * count + i] = (f & FLAG_INIT) ? 1 : 0;   // single-rate: history holds one entry
+    }
+    return QEKF_OK;
+}
+
+int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x16, const double *P)
+{
+    if (!range_ok(h, first, count) || !x16 || !P) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL input");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = store_rows(h, h->x, 16, first, count, x16);
+    if (rc) return rc;
+    const int n = h->nstates;
+    std::vector<double> packed((size_t)h->np * (size_t)count);
+    int e = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a; b < n; ++b, ++e)
+            std::memcpy(packed.data() + (size_t)e * (size_t)count, P + ((size_t)a * n + b) * (size_t)count, (size_t)count * 8);
+    rc = store_rows(h, h->P, h->np, first, count, packed.data());
+    if (rc) return rc;
+    std::vector<int32_t> fl((size_t)count);
+    CUDA_TRY(cudaMemcpy(fl.data(), h->flags + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    for (auto &f : fl) f |= FLAG_INIT;
+    CUDA_TRY(cudaMemcpy(h->flags + first, fl.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+    return QEKF_OK;
+}
+
+// ---- stateless step functions ------------------------------------------------------------------------
+
+static int stage_rows(qekf_handle *h, const double *host, int rows)
+{
+    // [rows][N] host -> [rows][ld] device slab in d_in
+    int rc = ensure_in(h, (size_t)rows * (size_t)h->ld * 8);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_in, (size_t)h->ld * 8, host, (size_t)h->n * 8, (size_t)h->n * 8, (size_t)rows,
+                               cudaMemcpyHostToDevice, h->stream));
+    return QEKF_OK;
+}
+
+int qekf_prediction_step(qekf_handle *h, const double *u)
+{
+    if (!h || !u) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = stage_rows(h, u, 6);
+    if (rc) return rc;
+#define CALL_PRED(T, B, D)                                                                                    \
+    do {                                                                                                      \
+        auto kern = predict_kernel<T, B, BLOCK>;                                                              \
+        int rc__ = prep_kernel(kern, smem_bytes(h));                                                          \
+        if (rc__) return rc__;                                                                                \
+        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in); \
+    } while (0)
+    QEKF_DISPATCH(h, CALL_PRED);
+#undef CALL_PRED
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return QEKF_OK;
+}
+
+int qekf_correction_step(qekf_handle *h, const double *tag_pose)
+{
+    if (!h || !tag_pose) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = stage_rows(h, tag_pose, 7);
+    if (rc) return rc;
+#define CALL_CORR(T, B, D)                                                                                    \
+    do {                                                                                                      \
+        auto kern = correct_kernel<T, B, D, BLOCK>;                                                           \
+        int rc__ = prep_kernel(kern, smem_bytes(h));                                                          \
+        if (rc__) return rc__;                                                                                \
+        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in); \
+    } while (0)
+    QEKF_DISPATCH(h, CALL_CORR);
+#undef CALL_CORR
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return QEKF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+"""ctypes loader for the host-instantiated product core (tests/host_core/host_core.cu).  TEST ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libhost_core.so")
+_SRC = [os.path.join(_HERE, "host_core.cu")] + [
+    os.path.join(_HERE, "..", "..", "quadrotor_landing_b200", "csrc", f)
+    for f in ("ekf_core.cuh", "ekf_kernels.cuh", "ekf_params.hpp")
+]
+
+
+def build(force=False):
+    stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRC)
+    if force or stale:
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", _LIB, _SRC[0]], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def prediction_step(params, x, P, u, prec=64):
+    n = 15 if params.est_bias else 9
+    x = _f64(x); P = _f64(P); u = _f64(u)
+    xo = np.zeros(16); Po = np.zeros((n, n)); acc = np.zeros(3)
+    lib().hc_prediction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(u), _dp(xo), _dp(Po), _dp(acc))
+    return xo, Po, acc
+
+
+def correction_step(params, x, P, tag, prec=64):
+    n = 15 if params.est_bias else 9
+    x = _f64(x); P = _f64(P); tag = _f64(tag)
+    xo = np.zeros(16); Po = np.zeros((n, n)); obs = np.zeros(7)
+    lib().hc_correction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(tag), _dp(xo), _dp(Po), _dp(obs))
+    return xo, Po, obs
+
+
+class HostBatch:
+    """N filters advanced by the product's run_filter() on the host (state kept in numpy arrays)."""
+
+    def __init__(self, params, n_filters, prec=64):
+        self.p = params
+        self.N = int(n_filters)
+        self.prec = prec
+        self.n = 15 if params.est_bias else 9
+        self.np_ = self.n * (self.n + 1) // 2
+        self.x = np.zeros((16, self.N)); self.x[9] = 1.0
+        self.Ppk = np.zeros((self.np_, self.N))
+        self.aux = np.zeros((11, self.N)); self.aux[9] = 1.0
+        self.pend = np.zeros((8, self.N))
+        self.flags = np.zeros(self.N, dtype=np.int32)
+        self.upds = np.zeros(self.N, dtype=np.int32)
+
+    def run(self, k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid=None, t_start=0.0):
+        imu = _f64(imu); tag_pose = _f64(tag_pose); tag_stamp = _f64(tag_stamp)
+        tag_step = np.ascontiguousarray(tag_step, dtype=np.int32)
+        M = tag_step.shape[0]
+        vptr = None
+        if tag_valid is not None:
+            tag_valid = np.ascontiguousarray(tag_valid, dtype=np.uint8)
+            vptr = tag_valid.ctypes.data_as(C.POINTER(C.c_uint8))
+        L = lib()
+        L.hc_run.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.c_int64,
+                             C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                             C.POINTER(C.c_uint8), C.c_double] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)] * 2
+        L.hc_run(C.byref(self.p), int(self.prec), self.N, int(k0), int(n_steps), _dp(imu), M,
+                 tag_step.ctypes.data_as(C.POINTER(C.c_int32)), _dp(tag_pose), _dp(tag_stamp), vptr, float(t_start),
+                 _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
+                 self.flags.ctypes.data_as(C.POINTER(C.c_int32)), self.upds.ctypes.data_as(C.POINTER(C.c_int32)))
+
+    def state(self):
+        return self.x.copy()
+
+    def cov(self):
+        n = self.n
+        P = np.zeros((n, n, self.N))
+        e = 0
+        for a in range(n):
+            for b in range(a, n):
+                P[a, b] = self.Ppk[e]; P[b, a] = self.Ppk[e]; e += 1
+        return P
