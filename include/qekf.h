@@ -162,6 +162,29 @@ int qekf_prediction_step(qekf_handle *h, const double *u);
 /* correction_step (src/relative_pose_EKF.cpp:417-502) with per-filter tag pose [7][N] (host). */
 int qekf_correction_step(qekf_handle *h, const double *tag_pose);
 
+/* ---- synthetic landing scenario (host; no reference equivalent: the reference was fed by Gazebo) ---- */
+/* Hover `hover_s` at z_start, then smooth-step descent to z_end; lateral sway x = ax sin(wx t),
+ * y = ay sin(wy t + phase); yaw = amp sin(w t).  The truth is advanced with the filter's own discrete
+ * kinematics (src/relative_pose_EKF.cpp:365-371) and measurements are the inverse of its measurement
+ * model (src/relative_pose_EKF.cpp:310-313,431-443), so a noise-free replay converges onto the truth. */
+typedef struct qekf_scenario_spec {
+    double duration_s, hover_s;
+    double z_start, z_end;
+    double sway_ax, sway_wx, sway_ay, sway_wy, sway_phase_y;
+    double yaw_amp, yaw_w;
+    double tag_rate_hz;      /* tag arrivals per second */
+    double tag_latency_s;    /* capture -> arrival latency (0 for the single-rate filter) */
+    double t_start;          /* time of tick 0 */
+} qekf_scenario_spec;
+
+int qekf_scenario_default(qekf_scenario_spec *s);
+/* T = ticks, M = tag arrivals for this (params, spec). */
+int qekf_scenario_sizes(const qekf_params *p, const qekf_scenario_spec *s, int64_t *T, int64_t *M);
+/* HOST outputs: truth [T+1][10] (r, v, q_tv after j ticks; the state after tick k is truth[k+1]),
+ * imu_clean [T][6], tag_step [M], tag_pose_clean [M][7], tag_stamp [M]. */
+int qekf_scenario_generate(const qekf_params *p, const qekf_scenario_spec *s, double *truth, double *imu_clean,
+                           int32_t *tag_step, double *tag_pose_clean, double *tag_stamp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 
 #include "ekf_kernels.cuh"
 #include "ekf_params.hpp"
+#include "scenario.hpp"
 
 using namespace qekf;
 
@@ -628,6 +629,35 @@ int qekf_correction_step(qekf_handle *h, const double *tag_pose)
 #undef CALL_CORR
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    return QEKF_OK;
+}
+
+// ---- synthetic scenario (host) -----------------------------------------------------------------------
+
+int qekf_scenario_default(qekf_scenario_spec *s)
+{
+    if (!s) return fail(QEKF_ERR_BAD_ARG, "spec is NULL");
+    qekf::scenario::defaults(s);
+    return QEKF_OK;
+}
+
+int qekf_scenario_sizes(const qekf_params *p, const qekf_scenario_spec *s, int64_t *T, int64_t *M)
+{
+    if (!p || !s || !T || !M) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (!(p->update_freq > 0) || !(s->tag_rate_hz > 0) || s->tag_rate_hz > p->update_freq)
+        return fail(QEKF_ERR_BAD_ARG, "need 0 < tag_rate_hz <= update_freq");
+    qekf::scenario::sizes(*p, *s, T, M);
+    return QEKF_OK;
+}
+
+int qekf_scenario_generate(const qekf_params *p, const qekf_scenario_spec *s, double *truth, double *imu_clean,
+                           int32_t *tag_step, double *tag_pose_clean, double *tag_stamp)
+{
+    if (!p || !s || !truth || !imu_clean || !tag_step || !tag_pose_clean || !tag_stamp)
+        return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (!(p->update_freq > 0) || !(s->tag_rate_hz > 0) || s->tag_rate_hz > p->update_freq)
+        return fail(QEKF_ERR_BAD_ARG, "need 0 < tag_rate_hz <= update_freq");
+    qekf::scenario::generate(*p, *s, truth, imu_clean, tag_step, tag_pose_clean, tag_stamp);
     return QEKF_OK;
 }
 

@@ -1,0 +1,122 @@
+"""CPU tier: the product's per-filter code (ekf_core.cuh + run_filter), instantiated for the host by
+tests/host_core, against the dense oracle.  Same templates as the CUDA kernels; no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+import host_core as hc
+import quadrotor_landing_b200 as q
+from oracle import ekf_oracle as orc
+from quadrotor_landing_b200 import scenario
+from streams_np import noisy_streams, norm_rel, rotors_params
+
+TOL = 1e-9   # BASELINE.json north_star: FP64 within 1e-9 relative on state and covariance
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "prototype_vectors.npz"))
+
+
+def rand_case(rng, n, est_bias):
+    x = np.zeros(16)
+    x[0:3] = rng.normal(size=3) + [0, 0, 2]
+    x[3:6] = rng.normal(scale=0.5, size=3)
+    qq = rng.normal(size=4); qq /= np.linalg.norm(qq)
+    x[6:10] = -qq if qq[3] < -0.75 else qq
+    if est_bias:
+        x[10:13] = rng.normal(scale=0.05, size=3)
+        x[13:16] = rng.normal(scale=0.005, size=3)
+    A = rng.normal(size=(n, n))
+    P = 0.1 * (A @ A.T / n + 0.5 * np.eye(n))
+    u = np.concatenate([rng.normal(size=3) + [0, 0, 9.8], rng.normal(scale=0.3, size=3)])
+    return x, P, u
+
+
+@pytest.mark.parametrize("est_bias", [1, 0])
+@pytest.mark.parametrize("direct", [1, 0])
+def test_steps_match_oracle(est_bias, direct):
+    rng = np.random.default_rng(7)
+    p = q.default_params()
+    p.est_bias, p.direct_orien_method = est_bias, direct
+    p.ab_static[0], p.wb_static[1] = 0.2, -0.01
+    f = orc.Filter(orc.params_from(p))
+    qvc = orc.quat_norm(np.array(list(p.q_vc)))
+    for t in range(40):
+        x, P, u = rand_case(rng, f.n, est_bias)
+        if t == 0:
+            u[3:6] = x[13:16] + np.array(list(p.wb_static))     # zero rate: small-angle branch
+        xo, Po, acc = f.prediction_step(x, P, u)
+        xh, Ph, ah = hc.prediction_step(p, x, P, u)
+        assert norm_rel(xh, xo) < TOL and norm_rel(Ph, Po) < TOL and norm_rel(ah, acc) < TOL
+        qt = orc.quat_mul(x[6:10], orc.quat_exp(rng.normal(scale=0.05 if t % 2 else 1.0, size=3)))
+        q_ct = orc.quat_mul(qt, qvc) * np.array([-1, -1, -1, 1.0])
+        tag = np.concatenate([rng.normal(scale=0.5, size=3) + [0, 0, 2], q_ct])
+        xc, Pc = f.correction_step(x, P, tag[:3], tag[3:])
+        xh, Ph, obs = hc.correction_step(p, x, P, tag)
+        assert norm_rel(xh, xc) < TOL and norm_rel(Ph, Pc) < TOL
+        a = f.aux()
+        assert norm_rel(obs[0:3], a["r_t_vt_obs"]) < TOL and norm_rel(obs[3:7], a["q_tv_obs"]) < TOL
+        assert np.max(np.abs(Ph - Ph.T)) == 0.0
+
+
+@pytest.mark.parametrize("est_bias,direct", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_replay_matches_oracle(est_bias, direct):
+    """3000 ticks of the hover-and-descend scenario, 6 filters with independent noise, a common and a
+    per-filter dropout window, replayed in three chunks (a latched measurement must survive the cut)."""
+    p = rotors_params(q.default_params(), est_bias=est_bias, direct=direct)
+    scn = scenario.generate(p)
+    N, T = 6, 3000
+    st = noisy_streams(scn, N, seed=11, T=T, dropout=(1000, 1400), random_dropout_ticks=200)
+    ob = orc.Batch(orc.params_from(p), N)
+    hb = hc.HostBatch(p, N)
+    for k0, n in ((0, 1003), (1003, 998), (2001, 999)):
+        ob.run(k0, n, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        hb.run(k0, n, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        assert norm_rel(hb.state(), ob.state()) < TOL
+        assert norm_rel(hb.cov(), ob.cov()) < TOL
+        fl = ob.flags()
+        assert np.array_equal(hb.upds, fl[4])
+        assert np.array_equal(hb.flags & 1, fl[0]) and np.array_equal((hb.flags >> 1) & 1, fl[1])
+    npred, ncorr = ob.counts()
+    assert ncorr > 200 * N // 2
+    # the filter actually tracks the truth (sanity of the scenario's inverse measurement model)
+    err = ob.state()[0:3] - scn.truth[T][0:3, None]
+    assert np.max(np.abs(err)) < 0.1
+
+
+@pytest.mark.parametrize("name,est_bias", [("seq_sr", True)])
+def test_replay_matches_prototype_golden(name, est_bias):
+    """The reference prototype's single-rate sequence, through the product's sequencer."""
+    p = q.default_params()
+    p.update_freq, p.measurement_freq = 100.0, float(G["seq_measurement_freq"])
+    p.limit_measurement_freq = p.corner_margin_enbl = p.direct_orien_method = 1
+    p.est_bias = int(est_bias)
+    imu, steps, poses = G[name + "_imu"], G[name + "_tag_step"], G[name + "_tag_pose"]
+    T = imu.shape[0]
+    hb = hc.HostBatch(p, 1)
+    worst = 0.0
+    for k in range(0, T, 50):
+        hb.run(k, 50, imu[:, :, None], steps, poses[:, :, None], np.zeros(len(steps)))
+        if G[name + "_active"][k + 49]:
+            worst = max(worst, norm_rel(hb.state()[:, 0], G[name + "_x"][k + 49]))
+            assert hb.upds[0] == G[name + "_upds"][k + 49]
+    assert norm_rel(hb.cov()[:, :, 0], G[name + "_P_last"]) < TOL
+    assert worst < TOL
+
+
+def test_fp32_host_instantiation_is_close():
+    """FP32 mode: same templates in float; single steps stay within 1e-4 of the FP64 oracle."""
+    rng = np.random.default_rng(3)
+    p = q.default_params()
+    p.direct_orien_method = 1
+    f = orc.Filter(orc.params_from(p))
+    qvc = orc.quat_norm(np.array(list(p.q_vc)))
+    for t in range(20):
+        x, P, u = rand_case(rng, 15, 1)
+        xo, Po, _ = f.prediction_step(x, P, u)
+        xh, Ph, _ = hc.prediction_step(p, x, P, u, prec=32)
+        assert norm_rel(xh, xo) < 1e-5 and norm_rel(Ph, Po) < 1e-5
+        qt = orc.quat_mul(x[6:10], orc.quat_exp(rng.normal(scale=0.05, size=3)))
+        q_ct = orc.quat_mul(qt, qvc) * np.array([-1, -1, -1, 1.0])
+        tag = np.concatenate([rng.normal(scale=0.5, size=3) + [0, 0, 2], q_ct])
+        xc, Pc = f.correction_step(x, P, tag[:3], tag[3:])
+        xh, Ph, _ = hc.correction_step(p, x, P, tag, prec=32)
+        assert norm_rel(xh, xc) < 1e-4 and norm_rel(Ph, Pc) < 1e-4

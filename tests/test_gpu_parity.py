@@ -1,0 +1,150 @@
+"""GPU tier: the CUDA path through the C ABI (libqekf.so) against the CPU oracle on the same seeded
+inputs.  FP64 tolerance 1e-9 norm-relative on state and covariance (BASELINE.json north_star); FP32
+mode 1e-4."""
+import os
+
+import numpy as np
+import pytest
+
+import quadrotor_landing_b200 as q
+from oracle import ekf_oracle as orc
+from quadrotor_landing_b200 import scenario
+from streams_np import noisy_streams, norm_rel, rotors_params
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "prototype_vectors.npz"))
+
+
+def rand_batch(rng, N, n, est_bias):
+    x = np.zeros((16, N))
+    x[0:3] = rng.normal(size=(3, N)) + np.array([0, 0, 2.0])[:, None]
+    x[3:6] = rng.normal(scale=0.5, size=(3, N))
+    qq = rng.normal(size=(4, N)); qq /= np.linalg.norm(qq, axis=0)
+    qq[:, qq[3] < -0.75] *= -1
+    x[6:10] = qq
+    if est_bias:
+        x[10:13] = rng.normal(scale=0.05, size=(3, N))
+        x[13:16] = rng.normal(scale=0.005, size=(3, N))
+    A = rng.normal(size=(N, n, n))
+    P = 0.1 * (A @ A.transpose(0, 2, 1) / n + 0.5 * np.eye(n))
+    u = np.concatenate([rng.normal(size=(3, N)) + np.array([0, 0, 9.8])[:, None], rng.normal(scale=0.3, size=(3, N))])
+    return x, np.ascontiguousarray(P.transpose(1, 2, 0)), u
+
+
+@pytest.mark.parametrize("est_bias,direct", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_step_functions_match_oracle(est_bias, direct):
+    rng = np.random.default_rng(5)
+    N = 100    # not a multiple of 32: exercises the ragged last warp
+    p = q.default_params()
+    p.est_bias, p.direct_orien_method = est_bias, direct
+    p.ab_static[0], p.wb_static[1] = 0.2, -0.01
+    b = q.BatchEKF(p, N)
+    n = b.n
+    f = orc.Filter(orc.params_from(p))
+    qvc = orc.quat_norm(np.array(list(p.q_vc)))
+    x, P, u = rand_batch(rng, N, n, est_bias)
+    b.set_state(x, P)
+    assert norm_rel(b.state(), x) == 0 and norm_rel(b.cov(), P) == 0
+    b.prediction_step(u)
+    xg, Pg, ag = b.state(), b.cov(), b.aux()
+    tag = np.zeros((7, N))
+    for i in range(N):
+        xo, Po, acc = f.prediction_step(x[:, i], P[:, :, i], u[:, i])
+        assert norm_rel(xg[:, i], xo) < TOL and norm_rel(Pg[:, :, i], Po) < TOL and norm_rel(ag[0:3, i], acc) < TOL
+        qt = orc.quat_mul(x[6:10, i], orc.quat_exp(rng.normal(scale=0.05 if i % 2 else 1.0, size=3)))
+        tag[3:7, i] = orc.quat_mul(qt, qvc) * np.array([-1, -1, -1, 1.0])
+        tag[0:3, i] = rng.normal(scale=0.5, size=3) + [0, 0, 2]
+    b.set_state(x, P)
+    b.correction_step(tag)
+    xg, Pg, ag = b.state(), b.cov(), b.aux()
+    for i in range(N):
+        xc, Pc = f.correction_step(x[:, i], P[:, :, i], tag[0:3, i], tag[3:7, i])
+        assert norm_rel(xg[:, i], xc) < TOL and norm_rel(Pg[:, :, i], Pc) < TOL
+        a = f.aux()
+        assert norm_rel(ag[3:6, i], a["r_t_vt_obs"]) < TOL and norm_rel(ag[6:10, i], a["q_tv_obs"]) < TOL
+    b.close()
+
+
+@pytest.mark.parametrize("est_bias,direct", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_replay_matches_oracle(est_bias, direct):
+    """Hover-and-descend scenario, independent noise per filter, common + per-filter dropouts, replayed in
+    three launches; compared after every launch."""
+    p = rotors_params(q.default_params(), est_bias=est_bias, direct=direct)
+    scn = scenario.generate(p)
+    N, T = 200, 3000
+    st = noisy_streams(scn, N, seed=21, T=T, dropout=(1000, 1400), random_dropout_ticks=200)
+    ob = orc.Batch(orc.params_from(p), N)
+    b = q.BatchEKF(p, N)
+    for k0, n in ((0, 1003), (1003, 998), (2001, 999)):
+        ob.run(k0, n, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        b.run(k0, n, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        assert norm_rel(b.state(), ob.state()) < TOL
+        assert norm_rel(b.cov(), ob.cov()) < TOL
+        assert norm_rel(b.aux()[0:10], ob.aux()[0:10]) < TOL
+        assert np.array_equal(b.flags()[0:5], ob.flags()[0:5])
+    assert ob.counts()[1] > 100 * N
+    b.close()
+
+
+def test_full_length_replay_4096_filters():
+    """BASELINE config 2 geometry at a size the oracle finishes in seconds: 512 filters x 12,000 ticks
+    (the 4096-filter replay is bench.py's parity leg)."""
+    p = rotors_params(q.default_params())
+    scn = scenario.generate(p)
+    N = 512
+    st = noisy_streams(scn, N, seed=33, dropout=(5000, 5400), random_dropout_ticks=200)
+    ob = orc.Batch(orc.params_from(p), N)
+    b = q.BatchEKF(p, N)
+    ob.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    b.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    assert norm_rel(b.state(), ob.state()) < TOL
+    assert norm_rel(b.cov(), ob.cov()) < TOL
+    Pg = b.cov()
+    assert np.all(np.linalg.eigvalsh(Pg.transpose(2, 0, 1)) > 0)      # every covariance is still SPD
+    err = b.state()[0:3] - scn.truth[scn.T][0:3, None]
+    assert np.sqrt(np.mean(err ** 2)) < 0.05
+    b.close()
+
+
+def test_per_tick_interface_matches_prototype_golden():
+    """N = 1 through the reference's per-tick interface (set_imu / set_tag / filter_update), against the
+    reference prototype's golden single-rate sequence."""
+    name = "seq_sr"
+    ekf = q.RelativePoseEKF()
+    ekf.update_freq, ekf.measurement_freq = 100.0, float(G["seq_measurement_freq"])
+    ekf.limit_measurement_freq = ekf.corner_margin_enbl = ekf.direct_orien_method = 1
+    ekf.initialize_params()
+    imu, steps, poses = G[name + "_imu"], G[name + "_tag_step"], G[name + "_tag_pose"]
+    m = 0
+    worst = 0.0
+    for k in range(300):
+        if m < len(steps) and steps[m] == k:
+            ekf.set_tag(poses[m, 0:3], poses[m, 3:7], 0.0)
+            m += 1
+        ekf.set_imu(imu[k, 0:3], imu[k, 3:6])
+        ekf.filter_update(k * 0.01)
+        assert ekf.state_initialized == bool(G[name + "_active"][k])
+        if not G[name + "_active"][k]:
+            continue
+        assert ekf.upds_since_correction == G[name + "_upds"][k]
+        x = np.concatenate([ekf.r_nom, ekf.v_nom, ekf.q_nom, ekf.ab_nom, ekf.wb_nom])
+        worst = max(worst, norm_rel(x, G[name + "_x"][k]))
+        if k % 10 == 0:
+            worst = max(worst, norm_rel(ekf.cov_pert, G[name + "_P"][k // 10]))
+    assert worst < TOL
+
+
+def test_fp32_mode_stays_close_and_spd():
+    p = rotors_params(q.default_params())
+    scn = scenario.generate(p)
+    N, T = 256, 4000
+    st = noisy_streams(scn, N, seed=41, T=T)
+    b64 = q.BatchEKF(p, N)
+    b32 = q.BatchEKF(p, N, precision=q.QEKF_FP32)
+    for b in (b64, b32):
+        b.run(0, T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    assert norm_rel(b32.state(), b64.state()) < 1e-4
+    assert norm_rel(b32.cov(), b64.cov()) < 1e-4
+    assert np.all(np.linalg.eigvalsh(b32.cov().transpose(2, 0, 1)) > 0)
+    b64.close(); b32.close()
