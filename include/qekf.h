@@ -162,6 +162,59 @@ int qekf_prediction_step(qekf_handle *h, const double *u);
 /* correction_step (src/relative_pose_EKF.cpp:417-502) with per-filter tag pose [7][N] (host). */
 int qekf_correction_step(qekf_handle *h, const double *tag_pose);
 
+/* ---- Monte-Carlo replay: one clean scenario shared by all filters, per-filter noise generated in-kernel ----
+ * (no reference equivalent: the reference runs one filter on live sensors).  The noise realisation of a
+ * filter depends only on (seed, global filter id, tick / arrival index): Philox4x32-10 keyed by the seed
+ * with counter (index, stream, id), Box-Muller normals.  IMU: u = clean + bias_i + sigma n.  Tag, in the
+ * camera frame like the filter's R_k = N R N^T (src/relative_pose_EKF.cpp:462-472): r_c += sigma_p n,
+ * q_ct <- exp(sigma_th n) (x) q_ct.  Dropouts: arrivals with dropout_k0 <= tag_step < dropout_k1 are lost
+ * for every filter, plus rand_dropout_len ticks starting at a per-filter uniform tick in [lo, hi). */
+typedef struct qekf_noise_spec {
+    uint64_t seed;
+    int64_t first_global_id;     /* global id of this handle's filter 0 (shards of one job share the id space) */
+    double sigma_accel, sigma_gyro;
+    double sigma_bias_accel, sigma_bias_gyro;
+    double sigma_tag_pos, sigma_tag_ang;
+    int32_t dropout_k0, dropout_k1;
+    int32_t rand_dropout_len, rand_dropout_lo, rand_dropout_hi;
+    int32_t reserved;
+} qekf_noise_spec;
+
+typedef struct qekf_shared_streams {
+    int64_t T;
+    const double *imu_clean;      /* [T][6] */
+    int64_t M;
+    const int32_t *tag_step;      /* [M] strictly increasing */
+    const double *tag_pose_clean; /* [M][7] */
+    const double *tag_stamp;      /* [M] */
+    const double *truth;          /* [T+1][10] r, v, q_tv; NULL = no statistics */
+    double t_start;
+    int32_t on_device;
+    int32_t reserved;
+} qekf_shared_streams;
+
+int qekf_noise_default(qekf_noise_spec *n);
+/* filter_update iterated n_steps times for every filter, inputs synthesised on the fly. */
+int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, int64_t k0,
+                         int64_t n_steps);
+/* The realisation of filters [first, first+count) as explicit streams in the qekf_streams layout, HOST
+ * outputs: imu [T][6][count], tag_pose [M][7][count], tag_valid [M][count], bias [6][count]. */
+int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, int64_t first,
+                            int64_t count, double *imu, double *tag_pose, uint8_t *tag_valid, double *bias);
+
+/* On-chip RMSE / NEES accumulation during qekf_run_monte_carlo: a sample is taken after tick k whenever
+ * (k+1) % stride == 0, into bin (k+1)/stride - 1.  Per bin, QEKF_STAT_DIM doubles:
+ *   [0..14] sum of squared error per error-state component (dr, dv, dtheta, dab, dwb)
+ *   [15] sum NEES  [16] samples  [17] samples with NEES inside the two-sided 95% chi-square interval
+ *   [18] diverged samples (non-finite state or covariance not SPD)  [19] sum |dr|^2 */
+#define QEKF_STAT_DIM 20
+int qekf_stats_configure(qekf_handle *h, int32_t n_bins, int32_t stride);
+int qekf_stats_reset(qekf_handle *h);
+int qekf_get_stats(qekf_handle *h, double *out /* host [n_bins][QEKF_STAT_DIM] */);
+/* Reduced statistics copied into a caller-owned DEVICE buffer [n_bins][QEKF_STAT_DIM] on the handle's
+ * stream, so that the caller can all-reduce them across GPUs (NCCL) without a host round trip. */
+int qekf_copy_stats_device(qekf_handle *h, void *dst_device);
+
 /* ---- synthetic landing scenario (host; no reference equivalent: the reference was fed by Gazebo) ---- */
 /* Hover `hover_s` at z_start, then smooth-step descent to z_end; lateral sway x = ax sin(wx t),
  * y = ay sin(wy t + phase); yaw = amp sin(w t).  The truth is advanced with the filter's own discrete

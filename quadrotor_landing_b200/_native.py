@@ -90,6 +90,36 @@ class QekfScenarioSpec(C.Structure):
         "yaw_amp", "yaw_w", "tag_rate_hz", "tag_latency_s", "t_start")]
 
 
+class QekfNoiseSpec(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("first_global_id", C.c_int64),
+        ("sigma_accel", C.c_double), ("sigma_gyro", C.c_double),
+        ("sigma_bias_accel", C.c_double), ("sigma_bias_gyro", C.c_double),
+        ("sigma_tag_pos", C.c_double), ("sigma_tag_ang", C.c_double),
+        ("dropout_k0", C.c_int32), ("dropout_k1", C.c_int32),
+        ("rand_dropout_len", C.c_int32), ("rand_dropout_lo", C.c_int32), ("rand_dropout_hi", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class QekfSharedStreams(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64),
+        ("imu_clean", C.c_void_p),
+        ("M", C.c_int64),
+        ("tag_step", C.c_void_p),
+        ("tag_pose_clean", C.c_void_p),
+        ("tag_stamp", C.c_void_p),
+        ("truth", C.c_void_p),
+        ("t_start", C.c_double),
+        ("on_device", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+STAT_DIM = 20
+
 # every symbol include/qekf.h declares; tests assert the library exports all of them
 EXPORTS = [
     "qekf_default_params", "qekf_create", "qekf_destroy", "qekf_set_params", "qekf_get_params",
@@ -98,6 +128,8 @@ EXPORTS = [
     "qekf_filter_update", "qekf_run", "qekf_get_state", "qekf_get_cov", "qekf_get_aux", "qekf_get_flags",
     "qekf_set_state", "qekf_prediction_step", "qekf_correction_step",
     "qekf_scenario_default", "qekf_scenario_sizes", "qekf_scenario_generate",
+    "qekf_noise_default", "qekf_run_monte_carlo", "qekf_synthesize_streams", "qekf_stats_configure",
+    "qekf_stats_reset", "qekf_get_stats", "qekf_copy_stats_device",
 ]
 
 _lib = None
@@ -141,6 +173,14 @@ def lib() -> C.CDLL:
     L.qekf_scenario_sizes.argtypes = [C.POINTER(QekfParams), C.POINTER(QekfScenarioSpec),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.qekf_scenario_generate.argtypes = [C.POINTER(QekfParams), C.POINTER(QekfScenarioSpec), dp, dp, ip, dp, dp]
+    L.qekf_noise_default.argtypes = [C.POINTER(QekfNoiseSpec)]
+    L.qekf_run_monte_carlo.argtypes = [vp, C.POINTER(QekfSharedStreams), C.POINTER(QekfNoiseSpec), C.c_int64, C.c_int64]
+    L.qekf_synthesize_streams.argtypes = [vp, C.POINTER(QekfSharedStreams), C.POINTER(QekfNoiseSpec), C.c_int64,
+                                          C.c_int64, dp, dp, C.POINTER(C.c_uint8), dp]
+    L.qekf_stats_configure.argtypes = [vp, C.c_int32, C.c_int32]
+    L.qekf_stats_reset.argtypes = [vp]
+    L.qekf_get_stats.argtypes = [vp, dp]
+    L.qekf_copy_stats_device.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -148,6 +188,12 @@ def lib() -> C.CDLL:
 def check(rc: int):
     if rc != 0:
         raise QekfError(rc, lib().qekf_last_error_string().decode("utf-8", "replace"))
+
+
+def default_noise() -> QekfNoiseSpec:
+    n = QekfNoiseSpec()
+    check(lib().qekf_noise_default(C.byref(n)))
+    return n
 
 
 def default_params() -> QekfParams:

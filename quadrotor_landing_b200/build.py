@@ -1,37 +1,67 @@
-"""In-tree build of libqekf.so with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""In-tree build of libqekf.so with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+The heavy kernel templates are split over translation units (one per real type x est_bias x
+direct_orien_method) that compile in parallel; objects go to quadrotor_landing_b200/build/.
+"""
 from __future__ import annotations
 
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(HERE, "build")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libqekf.so")
-SOURCES = ["qekf_capi.cu"]
-HEADERS = ["ekf_core.cuh", "ekf_kernels.cuh", "ekf_params.hpp", "scenario.hpp", os.path.join("..", "..", "include", "qekf.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+HEADERS = ["ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp", "scenario.hpp", "launch.hpp",
+           os.path.join("..", "..", "include", "qekf.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _units():
+    units = [("qekf_capi", "qekf_capi.cu", []), ("inst_misc", "inst_misc.cu", [])]
+    for t in ("double", "float"):
+        for b in (1, 0):
+            for d in (1, 0):
+                units.append(("inst_run_%s_b%d_d%d" % (t, b, d), "inst_run.cu",
+                              ["-DQ_T=%s" % t, "-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d]))
+    return units
 
 
 def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    srcs = HEADERS + ["qekf_capi.cu", "inst_misc.cu", "inst_run.cu"]
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in srcs)
+
+
+def _compile(unit, verbose):
+    name, src, defs = unit
+    obj = os.path.join(OBJ_DIR, name + ".o")
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (name, res.stdout))
+    return obj, res.stdout
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or is_stale()):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(10, os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda u: _compile(u, verbose), _units()))
+    objs = [r[0] for r in results]
     if verbose:
-        print(res.stdout)
+        for r in results:
+            print(r[1])
+    res = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout)
     return LIB
 
 

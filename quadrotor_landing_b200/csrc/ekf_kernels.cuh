@@ -8,6 +8,7 @@
 #pragma once
 
 #include "ekf_core.cuh"
+#include "ekf_synth.cuh"
 
 namespace qekf {
 
@@ -55,7 +56,125 @@ template <typename T> struct RunArgs {
     Consts<T> c;
     int64_t k0, n_steps;
     int32_t m0;           // first arrival with tag_step >= k0
+    NoiseSpec ns;         // SYNTH launches only
+    StatsView stats;      // SYNTH launches only (acc == nullptr: no statistics)
 };
+
+// Where a filter's inputs come from.  Explicit: per-filter (or shared) streams in memory.  Synth: one
+// clean stream shared by all filters plus this filter's own noise realisation, generated on the fly.
+template <typename T, bool SYNTH> struct Inputs {
+    const double *imu_i, *tag_i;
+    int64_t cs;
+    const uint8_t *valid_i;
+    int64_t vs;
+    const NoiseSpec *ns;
+    int64_t gid;
+    double bias[6];
+    int32_t priv_start;
+
+    QEKF_FN void init(const RunArgs<T> &a, int64_t i)
+    {
+        imu_i = a.in.imu + i * a.in.is;
+        tag_i = a.in.tag_pose + i * a.in.is;
+        cs = a.in.cs;
+        valid_i = a.in.tag_valid ? a.in.tag_valid + i : nullptr;
+        vs = a.in.vs;
+        ns = &a.ns;
+        gid = a.ns.gid0 + i;
+        if (SYNTH) {
+            true_bias(a.ns, gid, bias);
+            priv_start = private_dropout_start(a.ns, gid);
+        }
+    }
+    QEKF_FN void raw_imu(int64_t k, double u[6]) const
+    {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) u[cc] = imu_i[(k * 6 + cc) * cs];
+    }
+    // turn the raw (prefetched) sample of tick k into what the filter sees
+    QEKF_FN void imu(int64_t k, const double raw[6], T u[6]) const
+    {
+        if (SYNTH) {
+            double un[6];
+            synth_imu(*ns, gid, k, raw, bias, un);
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) u[cc] = (T)un[cc];
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) u[cc] = (T)raw[cc];
+        }
+    }
+    QEKF_FN void tag_f64(int32_t m, double tag[7]) const
+    {
+        double raw[7];
+#pragma unroll
+        for (int cc = 0; cc < 7; ++cc) raw[cc] = tag_i[((int64_t)m * 7 + cc) * cs];
+        if (SYNTH) synth_tag(*ns, gid, m, raw, tag);
+        else {
+#pragma unroll
+            for (int cc = 0; cc < 7; ++cc) tag[cc] = raw[cc];
+        }
+    }
+    QEKF_FN void tag(int32_t m, T t[7]) const
+    {
+        double d[7];
+        tag_f64(m, d);
+#pragma unroll
+        for (int cc = 0; cc < 7; ++cc) t[cc] = (T)d[cc];
+    }
+    QEKF_FN bool valid(int32_t m, int32_t step) const
+    {
+        if (SYNTH) return arrival_valid(*ns, step, priv_start);
+        return valid_i ? (valid_i[(int64_t)m * vs] != 0) : true;
+    }
+};
+
+// one statistics sample of one filter after tick k (SYNTH launches: the truth and the true bias are known)
+template <typename T, bool BIAS, class PS>
+QEKF_FN void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> &s, PS &P, const double bias[6])
+{
+    constexpr int N = PS::n;
+    constexpr int NP = N * (N + 1) / 2;
+    const StatsView &sv = a.stats;
+    const int64_t bin = (k + 1) / sv.stride - 1;
+    if (bin < 0 || bin >= sv.n_bins) return;
+    const double *tr = sv.truth + (k + 1) * 10;
+    T e[N];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { e[c] = (T)tr[c] - s.r[c]; e[3 + c] = (T)tr[3 + c] - s.v[c]; }
+    {
+        T qt[4] = { (T)tr[6], (T)tr[7], (T)tr[8], (T)tr[9] }, dq[4];
+        quat_conj_mul(s.q, qt, dq);
+        quat_normclip(dq);
+        quat_log(dq, e + 6);
+    }
+    if (BIAS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { e[9 + c] = (T)bias[c] - s.ab[c]; e[12 + c] = (T)bias[3 + c] - s.wb[c]; }
+    }
+    // save P, factor in place, restore
+    for (int el = 0; el < NP; ++el) a.st.P[el * a.st.ld + i] = P.el(el);
+    T nees;
+    bool ok = nees_inplace<T>(P, e, nees);
+    for (int el = 0; el < NP; ++el) P.el(el) = a.st.P[el * a.st.ld + i];
+    double esq = 0;
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < N; ++c) { finite = finite && (M<T>::abs_(e[c]) < T(1e30)); }
+    ok = ok && finite && (M<T>::abs_(nees) < T(1e30));
+    double *acc = sv.acc + (((i >> 5) % STAT_REPL) * (int64_t)sv.n_bins + bin) * STAT_DIM;
+    if (ok) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) stat_add(acc + c, (double)e[c] * (double)e[c]);
+        esq = (double)e[0] * (double)e[0] + (double)e[1] * (double)e[1] + (double)e[2] * (double)e[2];
+        stat_add(acc + 15, (double)nees);
+        stat_add(acc + 16, 1.0);
+        if ((double)nees >= sv.chi2_lo && (double)nees <= sv.chi2_hi) stat_add(acc + 17, 1.0);
+        stat_add(acc + 19, esq);
+    } else {
+        stat_add(acc + 18, 1.0);
+    }
+}
 
 template <typename T, class PS>
 QEKF_FN void load_filter(const DeviceState<T> &st, int64_t i, Nominal<T> &s, PS &P)
@@ -100,7 +219,7 @@ QEKF_FN void store_filter(const DeviceState<T> &st, int64_t i, const Nominal<T> 
 // ------------------------------------------------------------------------------------------------
 // The per-filter replay loop.  Host-callable so that the CPU-side unit tests (tests/host_core) can run
 // the very same code against the oracle without a GPU; the product only ever calls it from run_kernel.
-template <typename T, bool BIAS, bool DIRECT, class PS>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, class PS>
 QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
 {
     const Consts<T> &c = a.c;
@@ -114,33 +233,26 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
     int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     int32_t pend_m = -1;     // index of the latched arrival; -1 = latched pose lives in st.pend
 
-    const double *imu_i = a.in.imu + i * a.in.is;
-    const double *tag_i = a.in.tag_pose + i * a.in.is;
+    Inputs<T, SYNTH> in;
+    in.init(a, i);
 
     // software prefetch of the next tick's IMU sample
     double un[6];
-#pragma unroll
-    for (int cc = 0; cc < 6; ++cc) un[cc] = imu_i[(a.k0 * 6 + cc) * a.in.cs];
+    in.raw_imu(a.k0, un);
 
     for (int64_t k = a.k0; k < a.k0 + a.n_steps; ++k) {
         T u[6];
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) u[cc] = (T)un[cc];
-        if (k + 1 < a.k0 + a.n_steps) {
-#pragma unroll
-            for (int cc = 0; cc < 6; ++cc) un[cc] = imu_i[((k + 1) * 6 + cc) * a.in.cs];
-        }
+        in.imu(k, un, u);
+        if (k + 1 < a.k0 + a.n_steps) in.raw_imu(k + 1, un);
 
         // ---- AprilTagSubCallback for the arrival scheduled at this tick (node.cpp:153-176) ----
         if (k == next_tag_step) {
-            const bool valid = a.in.tag_valid ? (a.in.tag_valid[m * a.in.vs + i] != 0) : true;
-            if (valid) {
+            if (in.valid(m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     T tag[7];
-#pragma unroll
-                    for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)tag_i[((int64_t)m * 7 + cc) * a.in.cs];
+                    in.tag(m, tag);
                     initialize_state<T, BIAS>(s, P, tag, c, false);
                     flags |= FLAG_INIT;
                 }
@@ -155,8 +267,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
         T tag[7];
         if ((flags & FLAG_READY) && (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas)) {
             if (pend_m >= 0) {
-#pragma unroll
-                for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)tag_i[((int64_t)pend_m * 7 + cc) * a.in.cs];
+                in.tag(pend_m, tag);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
@@ -181,12 +292,17 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
             flags &= ~FLAG_CORRECTED;
         }
         flags |= FLAG_ACTIVE;
+        if (SYNTH) {
+            if (a.stats.acc && ((k + 1) % a.stats.stride) == 0) stats_sample<T, BIAS>(a, i, k, s, P, in.bias);
+        }
     }
 
     // a latched, still unconsumed measurement survives the launch in st.pend
     if ((flags & FLAG_READY) && pend_m >= 0) {
+        double tg[7];
+        in.tag_f64(pend_m, tg);
 #pragma unroll
-        for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tag_i[((int64_t)pend_m * 7 + cc) * a.in.cs];
+        for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
     }
     store_filter<T>(a.st, i, s, P);
@@ -197,7 +313,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
 }
 
 // fused multi-tick replay (single-rate filter: multirate_ekf = false)
-template <typename T, bool BIAS, bool DIRECT, int BLOCK>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunArgs<T> a)
 {
     constexpr int N = BIAS ? 15 : 9;
@@ -206,7 +322,7 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.st.n) return;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
-    run_filter<T, BIAS, DIRECT>(a, i, P);
+    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,6 +402,32 @@ __global__ void __launch_bounds__(BLOCK) correct_kernel(DeviceState<T> st, Const
     for (int cc = 0; cc < 3; ++cc) st.aux[(3 + cc) * st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) st.aux[(6 + cc) * st.ld + i] = obs.q_tv_obs[cc];
+}
+
+// The noise realisation of filters [first, first+count) written out as explicit streams in the C-ABI
+// layout (the checker replays exactly these through the oracle): imu [T][6][count], tag [M][7][count],
+// valid [M][count], bias [6][count].
+template <typename T>
+__global__ void synth_dump_kernel(RunArgs<T> a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,
+                                  double *tag_out, uint8_t *valid_out, double *bias_out)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Inputs<T, true> in;
+    in.init(a, first + j);
+    for (int c = 0; c < 6; ++c) bias_out[c * count + j] = in.bias[c];
+    for (int64_t k = 0; k < T_ticks; ++k) {
+        double raw[6], u[6];
+        in.raw_imu(k, raw);
+        synth_imu(a.ns, in.gid, k, raw, in.bias, u);
+        for (int c = 0; c < 6; ++c) imu_out[(k * 6 + c) * count + j] = u[c];
+    }
+    for (int32_t m = 0; m < a.in.M; ++m) {
+        double tg[7];
+        in.tag_f64(m, tg);
+        for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
+        valid_out[(int64_t)m * count + j] = in.valid(m, a.in.tag_step[m]) ? 1 : 0;
+    }
 }
 
 }  // namespace qekf

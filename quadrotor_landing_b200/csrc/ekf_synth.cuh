@@ -1,0 +1,194 @@
+// ekf_synth.cuh -- Monte-Carlo machinery the reference does not have (it runs one filter on live
+// sensors): counter-based per-filter noise realisations generated in-kernel, and on-chip accumulation
+// of RMSE / NEES statistics against the scenario truth.
+//
+// Noise: Philox4x32-10, key = 64-bit seed, counter = (index, stream tag, global filter id lo, hi), so a
+// realisation depends only on (seed, global filter id, tick/arrival index) -- never on the launch
+// geometry, the time chunking or the number of GPUs.  Normals by Box-Muller in FP32 (the FP32/SFU pipes
+// are idle while the FP64 pipe does the filter arithmetic), widened to the filter's real type.
+//
+// Measurement noise is applied in the camera frame, which is where the filter's R_k = N R N^T places it
+// (relative_pose_EKF.cpp:462-472):  r_c += n_p,  q_ct <- exp(n_th) (x) q_ct.
+#pragma once
+
+#include "ekf_core.cuh"
+
+namespace qekf {
+
+struct NoiseSpec {
+    uint64_t seed;
+    int64_t gid0;                 // global id of the handle's filter 0 (multi-GPU shards share one id space)
+    float sig_a, sig_w;           // IMU white noise (m/s^2, rad/s) per sample
+    float sig_ba, sig_bw;         // constant true bias drawn per filter
+    float sig_p, sig_th;          // tag position (m) and attitude (rad) noise
+    int32_t drop_k0, drop_k1;     // common dropout: arrivals with k0 <= tag_step < k1 are lost
+    int32_t rdrop_len, rdrop_lo, rdrop_hi;   // per-filter dropout of rdrop_len ticks starting in [lo, hi)
+};
+
+enum : uint32_t { STREAM_IMU = 0, STREAM_TAG = 2, STREAM_BIAS = 4, STREAM_DROPOUT = 6 };
+
+QEKF_FN uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+QEKF_FN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two standard normals from two 32-bit words (Box-Muller, FP32)
+QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
+{
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), never 0
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+#ifdef __CUDA_ARCH__
+    sincospif(2.0f * u2, &s, &c);
+#else
+    s = (float)::sin(6.283185307179586 * (double)u2);
+    c = (float)::cos(6.283185307179586 * (double)u2);
+#endif
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// six standard normals for (global filter id, stream, index)
+QEKF_FN void normals6(const NoiseSpec &ns, int64_t gid, uint32_t stream, uint32_t index, float z[6])
+{
+    uint32_t w0[4], w1[4];
+    const uint32_t k0 = (uint32_t)ns.seed, k1 = (uint32_t)(ns.seed >> 32);
+    const uint32_t g0 = (uint32_t)(uint64_t)gid, g1 = (uint32_t)((uint64_t)gid >> 32);
+    philox4x32_10(index, stream, g0, g1, k0, k1, w0);
+    philox4x32_10(index, stream + 1u, g0, g1, k0, k1, w1);
+    box_muller(w0[0], w0[1], z[0], z[1]);
+    box_muller(w0[2], w0[3], z[2], z[3]);
+    box_muller(w1[0], w1[1], z[4], z[5]);
+}
+
+// the constant true IMU bias of a filter
+QEKF_FN void true_bias(const NoiseSpec &ns, int64_t gid, double b[6])
+{
+    float z[6];
+    normals6(ns, gid, STREAM_BIAS, 0u, z);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        b[i] = (double)ns.sig_ba * (double)z[i];
+        b[3 + i] = (double)ns.sig_bw * (double)z[3 + i];
+    }
+}
+
+// first tick of the filter's private dropout window (or INT32_MAX when disabled)
+QEKF_FN int32_t private_dropout_start(const NoiseSpec &ns, int64_t gid)
+{
+    if (ns.rdrop_len <= 0 || ns.rdrop_hi <= ns.rdrop_lo) return INT32_MAX;
+    uint32_t w[4];
+    philox4x32_10(0u, STREAM_DROPOUT, (uint32_t)(uint64_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)ns.seed,
+                  (uint32_t)(ns.seed >> 32), w);
+    const uint32_t span = (uint32_t)(ns.rdrop_hi - ns.rdrop_lo);
+    return ns.rdrop_lo + (int32_t)mulhi32(w[0], span);
+}
+
+QEKF_FN bool arrival_valid(const NoiseSpec &ns, int32_t step, int32_t priv_start)
+{
+    if (step >= ns.drop_k0 && step < ns.drop_k1) return false;
+    if (priv_start != INT32_MAX && step >= priv_start && step < priv_start + ns.rdrop_len) return false;
+    return true;
+}
+
+// noisy IMU sample of tick k:  clean + bias + sigma * n          (doubles; the caller narrows)
+QEKF_FN void synth_imu(const NoiseSpec &ns, int64_t gid, int64_t k, const double clean[6], const double bias[6], double u[6])
+{
+    float z[6];
+    normals6(ns, gid, STREAM_IMU, (uint32_t)k, z);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        u[i] = clean[i] + bias[i] + (double)ns.sig_a * (double)z[i];
+        u[3 + i] = clean[3 + i] + bias[3 + i] + (double)ns.sig_w * (double)z[3 + i];
+    }
+}
+
+// noisy tag pose of arrival m:  r_c + sigma_p n,  exp(sigma_th n) (x) q_ct
+QEKF_FN void synth_tag(const NoiseSpec &ns, int64_t gid, int32_t m, const double clean[7], double tag[7])
+{
+    float z[6];
+    normals6(ns, gid, STREAM_TAG, (uint32_t)m, z);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tag[i] = clean[i] + (double)ns.sig_p * (double)z[i];
+    double v[3] = { (double)ns.sig_th * (double)z[3], (double)ns.sig_th * (double)z[4], (double)ns.sig_th * (double)z[5] };
+    double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double n = sqrt(n2);
+    double f = (n < 1e-10) ? 0.5 : sin(0.5 * n) / n;
+    double dq[4] = { v[0] * f, v[1] * f, v[2] * f, cos(0.5 * n) };
+    quat_mul<double>(dq, clean + 3, tag + 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------------
+constexpr int STAT_DIM = 20;      // 0..14 sum e_i^2 | 15 sum NEES | 16 samples | 17 NEES inside the two-sided
+                                  // 95% chi-square interval | 18 diverged (non-finite or P not SPD) | 19 sum |e_r|^2
+constexpr int STAT_REPL = 32;     // replicas of the accumulator (spreads atomic contention), summed on read
+
+struct StatsView {
+    double *acc;                  // [STAT_REPL][n_bins][STAT_DIM]
+    const double *truth;          // [T+1][10] r v q_tv; state after tick k is truth[k+1]
+    int32_t n_bins;
+    int32_t stride;               // sample after tick k when (k+1) % stride == 0
+    double chi2_lo, chi2_hi;
+};
+
+QEKF_FN void stat_add(double *addr, double v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(addr, v);
+#else
+    *addr += v;
+#endif
+}
+
+// NEES = e^T P^-1 e by an in-place packed Cholesky P = U^T U carried out IN the covariance storage.
+// The caller must have saved P elsewhere and must restore it afterwards.  Runtime loops on purpose: this
+// runs once every `stride` ticks and must not bloat the instruction footprint of the hot loop.
+template <typename T, class PS> QEKF_FN bool nees_inplace(PS &P, const T *e, T &nees)
+{
+    constexpr int N = PS::n;
+    T y[N];
+    nees = T(0);
+    bool ok = true;
+    for (int j = 0; j < N; ++j) {
+        T d = P.ld(j, j);
+        T yj = e[j];
+        for (int k = 0; k < j; ++k) {
+            const T ukj = P.ld(k, j);
+            d = M<T>::fma_(-ukj, ukj, d);
+            yj = M<T>::fma_(-ukj, y[k], yj);
+        }
+        if (!(d > T(0))) { ok = false; break; }
+        const T inv = T(1) / M<T>::sqrt_(d);
+        P.st(j, j, d * inv);
+        for (int i = j + 1; i < N; ++i) {
+            T v = P.ld(j, i);
+            for (int k = 0; k < j; ++k) v = M<T>::fma_(-P.ld(k, j), P.ld(k, i), v);
+            P.st(j, i, v * inv);
+        }
+        y[j] = yj * inv;
+        nees = M<T>::fma_(y[j], y[j], nees);
+    }
+    return ok;
+}
+
+}  // namespace qekf

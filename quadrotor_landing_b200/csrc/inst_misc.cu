@@ -1,0 +1,106 @@
+// inst_misc.cu -- the small single-step kernels, for every (real type, est_bias, direct) combination.
+#include "launch.hpp"
+
+namespace qekf {
+
+template <typename T, bool BIAS>
+cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
+                           int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream)
+{
+    auto kern = deliver_tag_kernel<T, BIAS, BLOCK>;
+    cudaError_t e = prep_kernel(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, BLOCK, smem, stream>>>(st, c, pose8, force_init, reinit_bias);
+    return cudaGetLastError();
+}
+
+template <typename T, bool BIAS>
+cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,
+                           cudaStream_t stream)
+{
+    auto kern = predict_kernel<T, BIAS, BLOCK>;
+    cudaError_t e = prep_kernel(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, BLOCK, smem, stream>>>(st, c, u);
+    return cudaGetLastError();
+}
+
+template <typename T, bool BIAS, bool DIRECT>
+cudaError_t launch_correct(const DeviceState<T> &st, const Consts<T> &c, const double *tag, unsigned grid, size_t smem,
+                           cudaStream_t stream)
+{
+    auto kern = correct_kernel<T, BIAS, DIRECT, BLOCK>;
+    cudaError_t e = prep_kernel(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, BLOCK, smem, stream>>>(st, c, tag);
+    return cudaGetLastError();
+}
+
+// q_nom = identity, q_tv_obs = identity, cov_pert = cov_init   (constructor, cpp:21,26 and :114)
+template <typename T> __global__ void reset_kernel(DeviceState<T> st, Consts<T> c, int nstates, int reset_nominal)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    if (reset_nominal) {
+        st.x[9 * st.ld + i] = T(1);
+        st.aux[9 * st.ld + i] = T(1);
+    }
+    int e = 0;
+    for (int a = 0; a < nstates; ++a)
+        for (int b = a; b < nstates; ++b, ++e) st.P[e * st.ld + i] = (a == b) ? c.cov_init[a / 3] : T(0);
+}
+
+template <typename T>
+cudaError_t launch_reset(const DeviceState<T> &st, const Consts<T> &c, int nstates, int reset_nominal, cudaStream_t stream)
+{
+    const unsigned g = (unsigned)((st.n + 127) / 128);
+    reset_kernel<T><<<g, 128, 0, stream>>>(st, c, nstates, reset_nominal);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_dump(const RunArgs<T> &a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,
+                        double *tag_out, uint8_t *valid_out, double *bias_out, cudaStream_t stream)
+{
+    const unsigned g = (unsigned)((count + 63) / 64);
+    synth_dump_kernel<T><<<g, 64, 0, stream>>>(a, first, count, T_ticks, imu_out, tag_out, valid_out, bias_out);
+    return cudaGetLastError();
+}
+
+__global__ void stats_reduce_kernel(const double *acc, double *out, int64_t n)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n * STAT_DIM) return;
+    double s = 0;
+    for (int r = 0; r < STAT_REPL; ++r) s += acc[(int64_t)r * n * STAT_DIM + j];
+    out[j] = s;
+}
+
+cudaError_t launch_stats_reduce(const double *acc, double *out, int64_t n, cudaStream_t stream)
+{
+    const int64_t tot = n * STAT_DIM;
+    stats_reduce_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, stream>>>(acc, out, n);
+    return cudaGetLastError();
+}
+
+#define INST_TB(T, B)                                                                                                   \
+    template cudaError_t launch_deliver<T, B>(const DeviceState<T> &, const Consts<T> &, const double *, int, int,      \
+                                              unsigned, size_t, cudaStream_t);                                         \
+    template cudaError_t launch_predict<T, B>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned,      \
+                                              size_t, cudaStream_t);                                                   \
+    template cudaError_t launch_correct<T, B, true>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned, \
+                                                    size_t, cudaStream_t);                                             \
+    template cudaError_t launch_correct<T, B, false>(const DeviceState<T> &, const Consts<T> &, const double *,         \
+                                                     unsigned, size_t, cudaStream_t);
+INST_TB(double, true)
+INST_TB(double, false)
+INST_TB(float, true)
+INST_TB(float, false)
+#define INST_T(T)                                                                                                       \
+    template cudaError_t launch_reset<T>(const DeviceState<T> &, const Consts<T> &, int, int, cudaStream_t);            \
+    template cudaError_t launch_dump<T>(const RunArgs<T> &, int64_t, int64_t, int64_t, double *, double *, uint8_t *,   \
+                                        double *, cudaStream_t);
+INST_T(double)
+INST_T(float)
+
+}  // namespace qekf

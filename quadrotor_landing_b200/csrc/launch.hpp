@@ -1,0 +1,45 @@
+// launch.hpp -- host-callable launchers, explicitly instantiated in inst_run.cu / inst_misc.cu so that the
+// heavy kernel templates compile in parallel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "ekf_kernels.cuh"
+
+namespace qekf {
+
+constexpr int BLOCK = 32;   // one warp per CTA: no intra-CTA synchronisation is ever needed
+
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH>
+cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);
+
+template <typename T, bool BIAS>
+cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
+                           int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream);
+
+template <typename T, bool BIAS>
+cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,
+                           cudaStream_t stream);
+
+template <typename T, bool BIAS, bool DIRECT>
+cudaError_t launch_correct(const DeviceState<T> &st, const Consts<T> &c, const double *tag, unsigned grid, size_t smem,
+                           cudaStream_t stream);
+
+template <typename T>
+cudaError_t launch_reset(const DeviceState<T> &st, const Consts<T> &c, int nstates, int reset_nominal, cudaStream_t stream);
+
+template <typename T>
+cudaError_t launch_dump(const RunArgs<T> &a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,
+                        double *tag_out, uint8_t *valid_out, double *bias_out, cudaStream_t stream);
+
+// acc [STAT_REPL][n][STAT_DIM] -> out [n][STAT_DIM]
+cudaError_t launch_stats_reduce(const double *acc, double *out, int64_t n, cudaStream_t stream);
+
+template <typename K> inline cudaError_t prep_kernel(K kernel, size_t smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+}  // namespace qekf

@@ -11,8 +11,8 @@
 #include <string>
 #include <vector>
 
-#include "ekf_kernels.cuh"
 #include "ekf_params.hpp"
+#include "launch.hpp"
 #include "scenario.hpp"
 
 using namespace qekf;
@@ -33,8 +33,6 @@ int fail(int code, const std::string &msg)
         if (e__ != cudaSuccess)                                                                     \
             return fail(QEKF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
     } while (0)
-
-constexpr int BLOCK = 32;   // one warp per CTA: no intra-CTA synchronisation is ever needed
 
 }  // namespace
 
@@ -61,6 +59,12 @@ struct qekf_handle {
     // cached device copies of host streams (qekf_run with on_device = 0)
     void *d_in = nullptr;
     size_t d_in_bytes = 0;
+    // Monte-Carlo statistics (device): acc [STAT_REPL][n_bins][STAT_DIM], reduced [n_bins][STAT_DIM]
+    double *stats_acc = nullptr, *stats_red = nullptr;
+    int32_t stats_bins = 0, stats_stride = 0;
+    // cached device copy of the shared clean scenario (qekf_run_monte_carlo with host pointers)
+    void *d_shared = nullptr;
+    size_t d_shared_bytes = 0;
     // launch bookkeeping
     int64_t launches = 0;
 };
@@ -77,14 +81,6 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
 
 size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize; }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
-
-template <typename K> int prep_kernel(K kernel, size_t smem)
-{
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
-    return QEKF_OK;
-}
 
 // dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision
 #define QEKF_DISPATCH(h, CALL)                                                             \
@@ -107,6 +103,8 @@ int free_state(qekf_handle *h)
 {
     cudaFree(h->x); cudaFree(h->P); cudaFree(h->aux); cudaFree(h->pend);
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
+    cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared);
+    h->stats_acc = h->stats_red = nullptr; h->stats_bins = 0; h->d_shared = nullptr; h->d_shared_bytes = 0;
     if (h->h_tick) cudaFreeHost(h->h_tick);
     h->x = h->P = h->aux = nullptr; h->pend = nullptr; h->flags = h->upds = nullptr;
     h->d_tick = nullptr; h->h_tick = nullptr; h->d_in = nullptr; h->d_in_bytes = 0;
@@ -136,28 +134,12 @@ int alloc_state(qekf_handle *h)
     return QEKF_OK;
 }
 
-// q_nom = identity, q_tv_obs = identity, cov_pert = cov_init   (constructor, cpp:21,26 and :114)
-template <typename T> __global__ void reset_kernel(DeviceState<T> st, Consts<T> c, int nstates, int reset_nominal)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st.n) return;
-    if (reset_nominal) {
-        st.x[9 * st.ld + i] = T(1);
-        st.aux[9 * st.ld + i] = T(1);
-    }
-    int e = 0;
-    for (int a = 0; a < nstates; ++a)
-        for (int b = a; b < nstates; ++b, ++e) st.P[e * st.ld + i] = (a == b) ? c.cov_init[a / 3] : T(0);
-}
-
 int reset_cov(qekf_handle *h, bool reset_nominal)
 {
-    const unsigned g = (unsigned)((h->n + 127) / 128);
     if (h->precision == QEKF_FP64)
-        reset_kernel<double><<<g, 128, 0, h->stream>>>(dstate<double>(h), make_consts<double>(h->p), h->nstates, reset_nominal);
+        CUDA_TRY(launch_reset<double>(dstate<double>(h), make_consts<double>(h->p), h->nstates, reset_nominal, h->stream));
     else
-        reset_kernel<float><<<g, 128, 0, h->stream>>>(dstate<float>(h), make_consts<float>(h->p), h->nstates, reset_nominal);
-    CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_reset<float>(dstate<float>(h), make_consts<float>(h->p), h->nstates, reset_nominal, h->stream));
     return QEKF_OK;
 }
 
@@ -171,25 +153,36 @@ int check_params(const qekf_params *p)
 }
 
 template <typename T, bool BIAS, bool DIRECT>
-int launch_run(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0)
+int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0, const NoiseSpec *ns,
+              const double *truth)
 {
     RunArgs<T> a;
+    std::memset(&a, 0, sizeof a);
     a.st = dstate<T>(h);
     a.in = in;
     a.c = make_consts<T>(h->p);
     a.k0 = k0; a.n_steps = n_steps; a.m0 = m0;
-    auto kern = run_kernel<T, BIAS, DIRECT, BLOCK>;
-    int rc = prep_kernel(kern, smem_bytes(h));
-    if (rc) return rc;
-    kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    if (ns) {
+        a.ns = *ns;
+        if (h->stats_acc && truth && h->stats_stride > 0) {
+            a.stats.acc = h->stats_acc; a.stats.truth = truth;
+            a.stats.n_bins = h->stats_bins; a.stats.stride = h->stats_stride;
+            // two-sided 95% chi-square interval for n degrees of freedom
+            a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
+            a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
+        }
+        CUDA_TRY((launch_run<T, BIAS, DIRECT, true>(a, grid_of(h), smem_bytes(h), h->stream)));
+    } else {
+        CUDA_TRY((launch_run<T, BIAS, DIRECT, false>(a, grid_of(h), smem_bytes(h), h->stream)));
+    }
     h->launches++;
     return QEKF_OK;
 }
 
-int run_dispatch(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0)
+int run_dispatch(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps, int32_t m0,
+                 const NoiseSpec *ns = nullptr, const double *truth = nullptr)
 {
-#define CALL_RUN(T, B, D) return launch_run<T, B, D>(h, in, k0, n_steps, m0)
+#define CALL_RUN(T, B, D) return run_typed<T, B, D>(h, in, k0, n_steps, m0, ns, truth)
     QEKF_DISPATCH(h, CALL_RUN);
 #undef CALL_RUN
     return QEKF_OK;
@@ -392,17 +385,11 @@ int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3])
 
 static int deliver(qekf_handle *h, int force_init, int reinit_bias)
 {
-#define CALL_DELIVER(T, B, D)                                                                          \
-    do {                                                                                               \
-        auto kern = deliver_tag_kernel<T, B, BLOCK>;                                                   \
-        int rc__ = prep_kernel(kern, smem_bytes(h));                                                   \
-        if (rc__) return rc__;                                                                         \
-        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p),      \
-                                                              h->d_tick + 8, force_init, reinit_bias); \
-    } while (0)
+#define CALL_DELIVER(T, B, D)                                                                                    \
+    CUDA_TRY((launch_deliver<T, B>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init, reinit_bias,   \
+                                   grid_of(h), smem_bytes(h), h->stream)))
     QEKF_DISPATCH(h, CALL_DELIVER);
 #undef CALL_DELIVER
-    CUDA_TRY(cudaGetLastError());
     h->launches++;
     return QEKF_OK;
 }
@@ -598,16 +585,11 @@ int qekf_prediction_step(qekf_handle *h, const double *u)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, u, 6);
     if (rc) return rc;
-#define CALL_PRED(T, B, D)                                                                                    \
-    do {                                                                                                      \
-        auto kern = predict_kernel<T, B, BLOCK>;                                                              \
-        int rc__ = prep_kernel(kern, smem_bytes(h));                                                          \
-        if (rc__) return rc__;                                                                                \
-        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in); \
-    } while (0)
+#define CALL_PRED(T, B, D)                                                                                   \
+    CUDA_TRY((launch_predict<T, B>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in, grid_of(h),  \
+                                   smem_bytes(h), h->stream)))
     QEKF_DISPATCH(h, CALL_PRED);
 #undef CALL_PRED
-    CUDA_TRY(cudaGetLastError());
     h->launches++;
     return QEKF_OK;
 }
@@ -618,17 +600,189 @@ int qekf_correction_step(qekf_handle *h, const double *tag_pose)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, tag_pose, 7);
     if (rc) return rc;
-#define CALL_CORR(T, B, D)                                                                                    \
-    do {                                                                                                      \
-        auto kern = correct_kernel<T, B, D, BLOCK>;                                                           \
-        int rc__ = prep_kernel(kern, smem_bytes(h));                                                          \
-        if (rc__) return rc__;                                                                                \
-        kern<<<grid_of(h), BLOCK, smem_bytes(h), h->stream>>>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in); \
-    } while (0)
+#define CALL_CORR(T, B, D)                                                                                      \
+    CUDA_TRY((launch_correct<T, B, D>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in, grid_of(h),  \
+                                      smem_bytes(h), h->stream)))
     QEKF_DISPATCH(h, CALL_CORR);
 #undef CALL_CORR
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    return QEKF_OK;
+}
+
+// ---- Monte-Carlo replay ---------------------------------------------------------------------------------
+
+int qekf_noise_default(qekf_noise_spec *n)
+{
+    if (!n) return fail(QEKF_ERR_BAD_ARG, "noise spec is NULL");
+    std::memset(n, 0, sizeof *n);
+    n->seed = 0x5EEDull;
+    n->sigma_accel = 0.02; n->sigma_gyro = 0.007;
+    n->sigma_bias_accel = 0.05; n->sigma_bias_gyro = 0.002;
+    n->sigma_tag_pos = 0.02; n->sigma_tag_ang = 0.01;
+    return QEKF_OK;
+}
+
+static NoiseSpec to_device_noise(const qekf_noise_spec &n)
+{
+    NoiseSpec d;
+    std::memset(&d, 0, sizeof d);
+    d.seed = n.seed; d.gid0 = n.first_global_id;
+    d.sig_a = (float)n.sigma_accel; d.sig_w = (float)n.sigma_gyro;
+    d.sig_ba = (float)n.sigma_bias_accel; d.sig_bw = (float)n.sigma_bias_gyro;
+    d.sig_p = (float)n.sigma_tag_pos; d.sig_th = (float)n.sigma_tag_ang;
+    d.drop_k0 = n.dropout_k0; d.drop_k1 = n.dropout_k1;
+    d.rdrop_len = n.rand_dropout_len; d.rdrop_lo = n.rand_dropout_lo; d.rdrop_hi = n.rand_dropout_hi;
+    return d;
+}
+
+// Build the kernel's view of a shared clean scenario; host arrays are staged into the handle's slab.
+static int shared_view(qekf_handle *h, const qekf_shared_streams *s, StreamView *in, const double **truth,
+                       std::vector<int32_t> *steps_host)
+{
+    if (!s->imu_clean || s->T <= 0) return fail(QEKF_ERR_BAD_ARG, "imu_clean is NULL or T <= 0");
+    if (s->M < 0 || (s->M > 0 && (!s->tag_step || !s->tag_pose_clean || !s->tag_stamp)))
+        return fail(QEKF_ERR_BAD_ARG, "tag streams are NULL");
+    const int64_t T = s->T, M = s->M;
+    steps_host->resize((size_t)M);
+    if (M > 0) {
+        if (s->on_device)
+            CUDA_TRY(cudaMemcpy(steps_host->data(), s->tag_step, (size_t)M * 4, cudaMemcpyDeviceToHost));
+        else
+            std::memcpy(steps_host->data(), s->tag_step, (size_t)M * 4);
+    }
+    for (int64_t m = 1; m < M; ++m)
+        if ((*steps_host)[m] <= (*steps_host)[m - 1]) return fail(QEKF_ERR_BAD_ARG, "tag_step must be strictly increasing");
+    std::memset(in, 0, sizeof *in);
+    in->cs = 1; in->is = 0; in->M = M; in->vs = 0;
+    in->t_start = s->t_start; in->update_freq = h->p.update_freq;
+    if (s->on_device) {
+        in->imu = s->imu_clean; in->tag_step = s->tag_step; in->tag_pose = s->tag_pose_clean;
+        in->tag_stamp = s->tag_stamp; *truth = s->truth;
+        return QEKF_OK;
+    }
+    const size_t imu_b = (size_t)T * 6 * 8, pose_b = (size_t)M * 7 * 8, stamp_b = (size_t)M * 8, step_b = (size_t)M * 4;
+    const size_t truth_b = s->truth ? (size_t)(T + 1) * 10 * 8 : 0;
+    const size_t o_imu = 0, o_pose = align_up(o_imu + imu_b, 256), o_stamp = align_up(o_pose + pose_b, 256);
+    const size_t o_step = align_up(o_stamp + stamp_b, 256), o_truth = align_up(o_step + step_b, 256);
+    const size_t total = align_up(o_truth + truth_b, 256);
+    if (total > h->d_shared_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_shared);
+        h->d_shared = nullptr; h->d_shared_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->d_shared, total));
+        h->d_shared_bytes = total;
+    }
+    char *d = (char *)h->d_shared;
+    CUDA_TRY(cudaMemcpyAsync(d + o_imu, s->imu_clean, imu_b, cudaMemcpyHostToDevice, h->stream));
+    if (M > 0) {
+        CUDA_TRY(cudaMemcpyAsync(d + o_pose, s->tag_pose_clean, pose_b, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(d + o_stamp, s->tag_stamp, stamp_b, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(d + o_step, s->tag_step, step_b, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (truth_b) CUDA_TRY(cudaMemcpyAsync(d + o_truth, s->truth, truth_b, cudaMemcpyHostToDevice, h->stream));
+    in->imu = (const double *)(d + o_imu); in->tag_pose = (const double *)(d + o_pose);
+    in->tag_stamp = (const double *)(d + o_stamp); in->tag_step = (const int32_t *)(d + o_step);
+    *truth = truth_b ? (const double *)(d + o_truth) : nullptr;
+    return QEKF_OK;
+}
+
+int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, int64_t k0,
+                         int64_t n_steps)
+{
+    if (!h || !s || !n) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (n_steps == 0) return QEKF_OK;
+    if (k0 < 0 || n_steps < 0 || k0 + n_steps > s->T) return fail(QEKF_ERR_BAD_ARG, "tick range outside the stream");
+    CUDA_TRY(cudaSetDevice(h->device));
+    StreamView in;
+    const double *truth = nullptr;
+    std::vector<int32_t> steps;
+    int rc = shared_view(h, s, &in, &truth, &steps);
+    if (rc) return rc;
+    int32_t m0 = 0;
+    for (size_t m = 0; m < steps.size(); ++m)
+        if (steps[m] < k0) m0 = (int32_t)(m + 1);
+    NoiseSpec ns = to_device_noise(*n);
+    return run_dispatch(h, in, k0, n_steps, m0, &ns, truth);
+}
+
+int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, int64_t first,
+                            int64_t count, double *imu, double *tag_pose, uint8_t *tag_valid, double *bias)
+{
+    if (!h || !s || !n || !imu || !bias) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (first < 0 || count <= 0) return fail(QEKF_ERR_BAD_ARG, "bad filter range");
+    if (s->M > 0 && (!tag_pose || !tag_valid)) return fail(QEKF_ERR_BAD_ARG, "NULL tag outputs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    StreamView in;
+    const double *truth = nullptr;
+    std::vector<int32_t> steps;
+    int rc = shared_view(h, s, &in, &truth, &steps);
+    if (rc) return rc;
+    const size_t imu_b = (size_t)s->T * 6 * (size_t)count * 8, tag_b = (size_t)s->M * 7 * (size_t)count * 8;
+    const size_t val_b = (size_t)s->M * (size_t)count, bias_b = 6 * (size_t)count * 8;
+    const size_t o_tag = align_up(imu_b, 256), o_val = align_up(o_tag + tag_b, 256), o_bias = align_up(o_val + val_b, 256);
+    rc = ensure_in(h, align_up(o_bias + bias_b, 256));
+    if (rc) return rc;
+    char *d = (char *)h->d_in;
+    RunArgs<double> a;
+    std::memset(&a, 0, sizeof a);
+    a.in = in;
+    a.ns = to_device_noise(*n);
+    CUDA_TRY(launch_dump<double>(a, first, count, s->T, (double *)d, (double *)(d + o_tag), (uint8_t *)(d + o_val),
+                                 (double *)(d + o_bias), h->stream));
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(imu, d, imu_b, cudaMemcpyDeviceToHost, h->stream));
+    if (s->M > 0) {
+        CUDA_TRY(cudaMemcpyAsync(tag_pose, d + o_tag, tag_b, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(tag_valid, d + o_val, val_b, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(bias, d + o_bias, bias_b, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QEKF_OK;
+}
+
+int qekf_stats_configure(qekf_handle *h, int32_t n_bins, int32_t stride)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    if (n_bins <= 0 || stride <= 0) return fail(QEKF_ERR_BAD_ARG, "n_bins and stride must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->stats_acc); cudaFree(h->stats_red);
+    h->stats_acc = h->stats_red = nullptr;
+    CUDA_TRY(cudaMalloc(&h->stats_acc, (size_t)STAT_REPL * n_bins * STAT_DIM * 8));
+    CUDA_TRY(cudaMalloc(&h->stats_red, (size_t)n_bins * STAT_DIM * 8));
+    h->stats_bins = n_bins; h->stats_stride = stride;
+    return qekf_stats_reset(h);
+}
+
+int qekf_stats_reset(qekf_handle *h)
+{
+    if (!h || !h->stats_acc) return fail(QEKF_ERR_NOT_INITIALIZED, "statistics are not configured");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemsetAsync(h->stats_acc, 0, (size_t)STAT_REPL * h->stats_bins * STAT_DIM * 8, h->stream));
+    return QEKF_OK;
+}
+
+int qekf_copy_stats_device(qekf_handle *h, void *dst_device)
+{
+    if (!h || !h->stats_acc) return fail(QEKF_ERR_NOT_INITIALIZED, "statistics are not configured");
+    if (!dst_device) return fail(QEKF_ERR_BAD_ARG, "destination is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_stats_reduce(h->stats_acc, h->stats_red, h->stats_bins, h->stream));
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(dst_device, h->stats_red, (size_t)h->stats_bins * STAT_DIM * 8, cudaMemcpyDeviceToDevice, h->stream));
+    return QEKF_OK;
+}
+
+int qekf_get_stats(qekf_handle *h, double *out)
+{
+    if (!h || !h->stats_acc) return fail(QEKF_ERR_NOT_INITIALIZED, "statistics are not configured");
+    if (!out) return fail(QEKF_ERR_BAD_ARG, "output is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(launch_stats_reduce(h->stats_acc, h->stats_red, h->stats_bins, h->stream));
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, h->stats_red, (size_t)h->stats_bins * STAT_DIM * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return QEKF_OK;
 }
 

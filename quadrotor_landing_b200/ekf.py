@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as nat
-from ._native import QekfParams, QekfStreams, check
+from ._native import QekfNoiseSpec, QekfParams, QekfSharedStreams, QekfStreams, check
 
 
 def _f64(a) -> np.ndarray:
@@ -131,6 +131,59 @@ class BatchEKF:
         s.t_start = float(t_start)
         s.on_device = 1
         check(self._L.qekf_run(self._h, C.byref(s), int(k0), int(n_steps)))
+
+    # ---- Monte-Carlo replay: shared clean scenario + in-kernel per-filter noise ----
+    def _shared(self, scn, with_truth=True):
+        """scn: quadrotor_landing_b200.scenario.Scenario (host numpy arrays).  Returns the C struct and the
+        arrays it points to (which must outlive the call)."""
+        imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp)
+        step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+        truth = _f64(scn.truth) if (with_truth and scn.truth is not None) else None
+        s = QekfSharedStreams()
+        s.T, s.imu_clean, s.M = imu.shape[0], imu.ctypes.data, step.shape[0]
+        s.tag_step, s.tag_pose_clean, s.tag_stamp = step.ctypes.data, pose.ctypes.data, stamp.ctypes.data
+        s.truth = truth.ctypes.data if truth is not None else None
+        s.t_start = float(scn.spec.t_start)
+        s.on_device = 0
+        return s, (imu, pose, stamp, step, truth)
+
+    def run_monte_carlo(self, scn, noise: QekfNoiseSpec, k0=0, n_steps=None, sync=True):
+        n_steps = scn.T - k0 if n_steps is None else n_steps
+        s, keep = self._shared(scn)
+        check(self._L.qekf_run_monte_carlo(self._h, C.byref(s), C.byref(noise), int(k0), int(n_steps)))
+        if sync:
+            self.sync()
+        return keep
+
+    def run_monte_carlo_device(self, shared: QekfSharedStreams, noise: QekfNoiseSpec, k0, n_steps):
+        """Device-resident shared scenario (shared.on_device = 1); asynchronous on the handle's stream."""
+        check(self._L.qekf_run_monte_carlo(self._h, C.byref(shared), C.byref(noise), int(k0), int(n_steps)))
+
+    def synthesize_streams(self, scn, noise: QekfNoiseSpec, first=0, count=None):
+        """The realisation of filters [first, first+count) as explicit host streams (qekf_streams layout)."""
+        count = self.N - first if count is None else count
+        s, keep = self._shared(scn, with_truth=False)
+        T, M = s.T, s.M
+        imu = np.zeros((T, 6, count)); pose = np.zeros((M, 7, count))
+        valid = np.zeros((M, count), dtype=np.uint8); bias = np.zeros((6, count))
+        check(self._L.qekf_synthesize_streams(self._h, C.byref(s), C.byref(noise), int(first), int(count), _dp(imu),
+                                              _dp(pose), valid.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(bias)))
+        return dict(imu=imu, tag_step=keep[3].copy(), tag_pose=pose, tag_stamp=keep[2].copy(), tag_valid=valid, bias=bias)
+
+    def stats_configure(self, n_bins: int, stride: int):
+        check(self._L.qekf_stats_configure(self._h, int(n_bins), int(stride)))
+        self._stats_bins = int(n_bins)
+
+    def stats_reset(self):
+        check(self._L.qekf_stats_reset(self._h))
+
+    def stats(self) -> np.ndarray:
+        out = np.zeros((self._stats_bins, nat.STAT_DIM))
+        check(self._L.qekf_get_stats(self._h, _dp(out)))
+        return out
+
+    def copy_stats_device(self, dst_ptr: int):
+        check(self._L.qekf_copy_stats_device(self._h, C.c_void_p(int(dst_ptr))))
 
     # ---- stateless steps ----
     def prediction_step(self, u):

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libhost_core.so")
 _SRC = [os.path.join(_HERE, "host_core.cu")] + [
     os.path.join(_HERE, "..", "..", "quadrotor_landing_b200", "csrc", f)
-    for f in ("ekf_core.cuh", "ekf_kernels.cuh", "ekf_params.hpp")
+    for f in ("ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp")
 ]
 
 
@@ -91,6 +91,22 @@ class HostBatch:
                  _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
                  self.flags.ctypes.data_as(C.POINTER(C.c_int32)), self.upds.ctypes.data_as(C.POINTER(C.c_int32)))
 
+    def run_mc(self, scn, noise, k0=0, n_steps=None, stats=None, stride=0):
+        """Monte-Carlo replay (shared clean scenario + per-filter noise).  stats: array [32][n_bins][20] or None."""
+        n_steps = scn.T - k0 if n_steps is None else n_steps
+        imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
+        step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+        L = lib()
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.hc_run_mc.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, dp,
+                                C.c_void_p, dp, C.c_int32, C.c_int32, C.c_double, dp, dp, dp, dp, ip, ip]
+        sp = _dp(stats) if stats is not None else None
+        nb = stats.shape[1] if stats is not None else 0
+        L.hc_run_mc(C.byref(self.p), int(self.prec), self.N, int(k0), int(n_steps), _dp(imu), step.shape[0],
+                    step.ctypes.data_as(ip), _dp(pose), _dp(stamp), _dp(truth), C.byref(noise), sp, nb, int(stride),
+                    float(scn.spec.t_start), _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
+                    self.flags.ctypes.data_as(ip), self.upds.ctypes.data_as(ip))
+
     def state(self):
         return self.x.copy()
 
@@ -102,3 +118,20 @@ class HostBatch:
             for b in range(a, n):
                 P[a, b] = self.Ppk[e]; P[b, a] = self.Ppk[e]; e += 1
         return P
+
+
+def synthesize(scn, noise, first, count):
+    """Explicit streams of filters [first, first+count) from the product's generator (host-instantiated)."""
+    imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean)
+    step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+    T, M = imu.shape[0], step.shape[0]
+    o_imu = np.zeros((T, 6, count)); o_tag = np.zeros((M, 7, count))
+    o_val = np.zeros((M, count), dtype=np.uint8); o_bias = np.zeros((6, count))
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L = lib()
+    L.hc_synthesize.argtypes = [C.c_void_p, C.c_int64, dp, C.c_int64, ip, dp, C.c_int64, C.c_int64, dp, dp,
+                                C.POINTER(C.c_uint8), dp]
+    L.hc_synthesize(C.byref(noise), T, _dp(imu), M, step.ctypes.data_as(ip), _dp(pose), int(first), int(count),
+                    _dp(o_imu), _dp(o_tag), o_val.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(o_bias))
+    return dict(imu=o_imu, tag_step=step.copy(), tag_pose=o_tag, tag_stamp=_f64(scn.tag_stamp).copy(), tag_valid=o_val,
+                bias=o_bias)

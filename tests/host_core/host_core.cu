@@ -61,10 +61,18 @@ template <typename T, bool BIAS, bool DIRECT> void correct_t(const qekf_params *
     for (int k = 0; k < 4; ++k) obs7[3 + k] = obs.q_tv_obs[k];
 }
 
+struct McArgs {           // Monte-Carlo (synthetic-noise) extras; ns == nullptr selects explicit streams
+    const NoiseSpec *ns;
+    const double *truth;
+    double *stats_acc;    // [STAT_REPL][n_bins][STAT_DIM]
+    int32_t n_bins, stride;
+};
+
 template <typename T, bool BIAS, bool DIRECT>
 void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
            const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
-           double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds)
+           double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+           const McArgs *mc = nullptr)
 {
     constexpr int NS = BIAS ? 15 : 9;
     constexpr int NP = NS * (NS + 1) / 2;
@@ -73,6 +81,7 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     for (size_t k = 0; k < Ps.size(); ++k) Ps[k] = (T)Ppk[k];
     for (size_t k = 0; k < as.size(); ++k) as[k] = (T)aux[k];
     RunArgs<T> a;
+    std::memset(&a, 0, sizeof a);
     a.st.x = xs.data(); a.st.P = Ps.data(); a.st.aux = as.data(); a.st.pend = pend;
     a.st.flags = flags; a.st.upds = upds; a.st.ld = N; a.st.n = N;
     std::memset(&a.in, 0, sizeof a.in);
@@ -84,9 +93,19 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     int32_t m0 = 0;
     while (m0 < M && tag_step[m0] < k0) ++m0;
     a.m0 = m0;
+    if (mc && mc->ns) {
+        a.in.cs = 1; a.in.is = 0; a.in.vs = 0; a.in.tag_valid = nullptr;
+        a.ns = *mc->ns;
+        if (mc->stats_acc && mc->truth) {
+            a.stats.acc = mc->stats_acc; a.stats.truth = mc->truth; a.stats.n_bins = mc->n_bins; a.stats.stride = mc->stride;
+            a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
+            a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
+        }
+    }
     for (int64_t i = 0; i < N; ++i) {
         PLocal<T, NS> P;
-        run_filter<T, BIAS, DIRECT>(a, i, P);
+        if (mc && mc->ns) run_filter<T, BIAS, DIRECT, true>(a, i, P);
+        else run_filter<T, BIAS, DIRECT, false>(a, i, P);
     }
     for (size_t k = 0; k < xs.size(); ++k) x[k] = xs[k];
     for (size_t k = 0; k < Ps.size(); ++k) Ppk[k] = Ps[k];
@@ -133,6 +152,60 @@ void hc_run(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_ste
 #define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds)
     HC_DISPATCH(prec, p, C_);
 #undef C_
+}
+
+// Monte-Carlo replay: shared clean streams imu [T][6], tag_pose [M][7]; noise generated per filter.
+// noise: the product's device NoiseSpec filled from the qekf_noise_spec fields.
+void hc_run_mc(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_steps, const double *imu_clean, int64_t M,
+               const int32_t *tag_step, const double *tag_pose_clean, const double *tag_stamp, const double *truth,
+               const qekf_noise_spec *n, double *stats_acc, int32_t n_bins, int32_t stride, double t_start, double *x,
+               double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds)
+{
+    NoiseSpec ns;
+    std::memset(&ns, 0, sizeof ns);
+    ns.seed = n->seed; ns.gid0 = n->first_global_id;
+    ns.sig_a = (float)n->sigma_accel; ns.sig_w = (float)n->sigma_gyro;
+    ns.sig_ba = (float)n->sigma_bias_accel; ns.sig_bw = (float)n->sigma_bias_gyro;
+    ns.sig_p = (float)n->sigma_tag_pos; ns.sig_th = (float)n->sigma_tag_ang;
+    ns.drop_k0 = n->dropout_k0; ns.drop_k1 = n->dropout_k1;
+    ns.rdrop_len = n->rand_dropout_len; ns.rdrop_lo = n->rand_dropout_lo; ns.rdrop_hi = n->rand_dropout_hi;
+    McArgs mc = { &ns, truth, stats_acc, n_bins, stride };
+#define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu_clean, M, tag_step, tag_pose_clean, tag_stamp, nullptr, t_start, x, Ppk, aux, pend, flags, upds, &mc)
+    HC_DISPATCH(prec, p, C_);
+#undef C_
+}
+
+// the product's generator, host-instantiated: explicit streams for filters [first, first+count)
+void hc_synthesize(const qekf_noise_spec *n, int64_t T, const double *imu_clean, int64_t M, const int32_t *tag_step,
+                   const double *tag_pose_clean, int64_t first, int64_t count, double *imu_out, double *tag_out,
+                   uint8_t *valid_out, double *bias_out)
+{
+    RunArgs<double> a;
+    std::memset(&a, 0, sizeof a);
+    a.in.imu = imu_clean; a.in.tag_pose = tag_pose_clean; a.in.tag_step = tag_step; a.in.cs = 1; a.in.is = 0; a.in.M = M;
+    a.ns.seed = n->seed; a.ns.gid0 = n->first_global_id;
+    a.ns.sig_a = (float)n->sigma_accel; a.ns.sig_w = (float)n->sigma_gyro;
+    a.ns.sig_ba = (float)n->sigma_bias_accel; a.ns.sig_bw = (float)n->sigma_bias_gyro;
+    a.ns.sig_p = (float)n->sigma_tag_pos; a.ns.sig_th = (float)n->sigma_tag_ang;
+    a.ns.drop_k0 = n->dropout_k0; a.ns.drop_k1 = n->dropout_k1;
+    a.ns.rdrop_len = n->rand_dropout_len; a.ns.rdrop_lo = n->rand_dropout_lo; a.ns.rdrop_hi = n->rand_dropout_hi;
+    for (int64_t j = 0; j < count; ++j) {
+        Inputs<double, true> in;
+        in.init(a, first + j);
+        for (int c = 0; c < 6; ++c) bias_out[c * count + j] = in.bias[c];
+        for (int64_t k = 0; k < T; ++k) {
+            double raw[6], u[6];
+            in.raw_imu(k, raw);
+            synth_imu(a.ns, in.gid, k, raw, in.bias, u);
+            for (int c = 0; c < 6; ++c) imu_out[(k * 6 + c) * count + j] = u[c];
+        }
+        for (int32_t m = 0; m < M; ++m) {
+            double tg[7];
+            in.tag_f64(m, tg);
+            for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
+            valid_out[(int64_t)m * count + j] = in.valid(m, tag_step[m]) ? 1 : 0;
+        }
+    }
 }
 
 }  // extern "C"

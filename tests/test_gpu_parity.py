@@ -9,6 +9,7 @@ import pytest
 import quadrotor_landing_b200 as q
 from oracle import ekf_oracle as orc
 from quadrotor_landing_b200 import scenario
+from oracle import noise_np
 from streams_np import noisy_streams, norm_rel, rotors_params
 
 pytestmark = pytest.mark.gpu
@@ -148,3 +149,88 @@ def test_fp32_mode_stays_close_and_spd():
     assert norm_rel(b32.cov(), b64.cov()) < 1e-4
     assert np.all(np.linalg.eigvalsh(b32.cov().transpose(2, 0, 1)) > 0)
     b64.close(); b32.close()
+
+
+def _short_scenario(p, seconds=8.0):
+    spec = scenario.default_spec()
+    spec.duration_s, spec.hover_s = seconds, 2.0
+    return scenario.generate(p, spec)
+
+
+def _noise(first=0):
+    n = q.default_noise()
+    n.first_global_id = first
+    n.dropout_k0, n.dropout_k1 = 600, 800
+    n.rand_dropout_len, n.rand_dropout_lo, n.rand_dropout_hi = 150, 100, 1200
+    return n
+
+
+def test_device_noise_generator_matches_numpy_restatement():
+    p = rotors_params(q.default_params())
+    scn = _short_scenario(p)
+    noise = _noise(first=123456789012)
+    b = q.BatchEKF(p, 64)
+    st = b.synthesize_streams(scn, noise, 3, 16)
+    ref = noise_np.synthesize(noise, scn.imu_clean, scn.tag_step, scn.tag_pose_clean, noise.first_global_id + 3 + np.arange(16))
+    assert np.max(np.abs(st["bias"] - ref["bias"])) < 1e-5 * noise.sigma_bias_accel
+    assert np.max(np.abs(st["imu"] - ref["imu"])) < 1e-5 * noise.sigma_accel
+    assert np.max(np.abs(st["tag_pose"] - ref["tag_pose"])) < 1e-5 * noise.sigma_tag_pos
+    assert np.array_equal(st["tag_valid"], ref["tag_valid"])
+    b.close()
+
+
+@pytest.mark.parametrize("est_bias,direct", [(1, 1), (0, 0)])
+def test_monte_carlo_replay_matches_oracle_and_explicit_path(est_bias, direct):
+    """In-kernel noise synthesis: (i) the oracle replaying the dumped realisation agrees to 1e-9, (ii) the
+    explicit-stream kernel fed the dumped realisation agrees BIT FOR BIT, (iii) the on-chip RMSE/NEES sums
+    agree with a numpy evaluation of the oracle's states."""
+    p = rotors_params(q.default_params(), est_bias=est_bias, direct=direct)
+    scn = _short_scenario(p)
+    noise = _noise(first=5000)
+    N, stride = 96, 400
+    nb = scn.T // stride
+    b = q.BatchEKF(p, N)
+    b.stats_configure(nb, stride)
+    b.run_monte_carlo(scn, noise, 0, 777)
+    b.run_monte_carlo(scn, noise, 777, scn.T - 777)
+    st = b.synthesize_streams(scn, noise, 0, N)
+    b2 = q.BatchEKF(p, N)
+    b2.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    assert np.array_equal(b.state(), b2.state()) and np.array_equal(b.cov(), b2.cov())
+    ob = orc.Batch(orc.params_from(p), N)
+    n = ob.n
+    ref = np.zeros((nb, 20))
+    lo, hi = (6.262137795043251, 27.488392863442982) if est_bias else (2.7003894999803584, 19.02276779864163)
+    for k in range(nb):
+        ob.run(k * stride, stride, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        e, nees = noise_np.error_stats(ob.state(), ob.cov(), scn.truth[(k + 1) * stride], st["bias"], n)
+        ref[k, 0:n] = (e ** 2).sum(axis=1)
+        ref[k, 15], ref[k, 16] = nees.sum(), N
+        ref[k, 17] = np.sum((nees >= lo) & (nees <= hi))
+        ref[k, 19] = (e[0:3] ** 2).sum()
+    assert norm_rel(b.state(), ob.state()) < TOL and norm_rel(b.cov(), ob.cov()) < TOL
+    stats = b.stats()
+    assert np.array_equal(stats[:, 16:19], ref[:, 16:19])
+    assert norm_rel(stats[:, 0:16], ref[:, 0:16]) < TOL and norm_rel(stats[:, 19], ref[:, 19]) < TOL
+    b.close(); b2.close()
+
+
+def test_monte_carlo_is_independent_of_sharding():
+    """Filters [0, N) in one handle == two handles owning [0, N/2) and [N/2, N) (what G GPUs would run)."""
+    p = rotors_params(q.default_params())
+    scn = _short_scenario(p, seconds=4.0)
+    N, stride = 128, 200
+    nb = scn.T // stride
+    full = q.BatchEKF(p, N); full.stats_configure(nb, stride)
+    full.run_monte_carlo(scn, _noise(0))
+    parts = []
+    tot = np.zeros((nb, 20))
+    for r in range(2):
+        h = q.BatchEKF(p, N // 2); h.stats_configure(nb, stride)
+        h.run_monte_carlo(scn, _noise(r * N // 2))
+        parts.append(h.state()); tot += h.stats()
+        h.close()
+    assert np.array_equal(np.concatenate(parts, axis=1), full.state())
+    assert np.array_equal(tot[:, 16:19], full.stats()[:, 16:19])
+    assert norm_rel(tot, full.stats()) < 1e-12
+    full.close()
