@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- EKF filter-steps/s (propagate + update) on B200, the metric of BASELINE.json.
+
+One "step" = one full pass of the hot path over one batch: every filter of the GPU replays the whole
+60 s hover-and-descend landing scenario (12,000 IMU ticks at 200 Hz, 1,800 tag arrivals at 30 Hz, a
+common 2 s tag dropout plus a private 1 s dropout per filter), FP64, noise generated in-kernel, RMSE/NEES
+statistics accumulated on-chip and -- at N > 1 -- all-reduced over NCCL.  Weak scaling: every GPU owns
+`--filters` (default 1,048,576) filters, BASELINE config 3 at N=1 and config 4 (8M filters) at N=8.
+
+  python bench.py --gpus 1 --steps K --warmup W                 (this repo's CUDA path)
+  python bench.py --impl reference --gpus N --steps K --warmup W (CPU restatement of the reference on
+                                                                 the box's host cores; rank 0 only)
+
+`value` is timed with CUDA events on the launching stream with every input resident in HBM; `e2e` is the
+same metric through the C ABI with HOST buffers (pinned), the host->device copies of the scenario and the
+device->host read of the statistics inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Floating-point operations executed per call by the structured code (FMA = 2), measured with an
+# instrumented scalar type (tests/host_core hc_count_flops; tests/test_flop_count.py pins these numbers).
+FLOPS = {(1, 1): (1384, 3425), (1, 0): (1384, 3911), (0, 1): (748, 2015), (0, 0): (748, 2231)}
+# Algorithmic HBM bytes per filter-step in Monte-Carlo mode: state + covariance load and store
+# (16 + 120 doubles each way) amortised over the ticks of one launch; the shared clean scenario is L2-resident.
+STATE_BYTES = (16 + 120) * 8 * 2
+
+
+def bench_params(q):
+    """rotors.yaml noises (quad_state_estimation/config/relative_pose_EKF_rotors.yaml:13-19) with the
+    benchmark rates of SURVEY.md section 8(d): 200 Hz update, 30 Hz tag, gated, single-rate, direct model."""
+    p = q.default_params()
+    p.update_freq, p.measurement_freq = 200.0, 30.0
+    p.measurement_delay, p.measurement_delay_max, p.dyn_measurement_delay_offset = 0.030, 0.200, 0.005
+    for i in range(3):
+        p.Q_a[i], p.Q_w[i], p.Q_ab[i], p.Q_wb[i] = 0.0005, 0.00005, 5.0e-5, 5.0e-6
+    p.R_r[0], p.R_r[1], p.R_r[2] = 0.015, 0.015, 0.020
+    p.R_ang[0], p.R_ang[1], p.R_ang[2] = 0.0015, 0.0015, 0.04
+    p.limit_measurement_freq = p.corner_margin_enbl = p.est_bias = p.direct_orien_method = 1
+    p.multirate_ekf = p.dynamic_meas_delay = 0
+    return p
+
+
+def bench_noise(q, first_global_id=0):
+    n = q.default_noise()                      # sigma: accel .02, gyro .007, bias .05/.002, tag .02 m/.01 rad
+    n.first_global_id = first_global_id
+    n.dropout_k0, n.dropout_k1 = 5000, 5400    # t in [25, 27) s
+    n.rand_dropout_len, n.rand_dropout_lo, n.rand_dropout_hi = 200, 400, 11600
+    return n
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) >= 7 and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
+
+
+def cpu_streams(q, scn, n_filters):
+    """Explicit noisy streams for the CPU legs (same noise model and seeds, numpy restatement of the generator)."""
+    from oracle import noise_np
+    st = noise_np.synthesize(bench_noise(q), scn.imu_clean, scn.tag_step, scn.tag_pose_clean, np.arange(n_filters))
+    return np.ascontiguousarray(st["imu"]), np.ascontiguousarray(st["tag_pose"]), st["tag_valid"]
+
+
+def cpu_replay(p, scn, streams, threads):
+    """One bounded CPU step: the dense restatement of the reference (oracle/) replays the whole scenario for
+    the sample's filters, OpenMP over filters.  Returns seconds."""
+    from oracle import ekf_oracle as orc
+    imu, pose, valid = streams
+    ob = orc.Batch(orc.params_from(p), imu.shape[2])
+    t0 = time.perf_counter()
+    ob.run(0, scn.T, imu, scn.tag_step, pose, scn.tag_stamp, valid, n_threads=threads)
+    return time.perf_counter() - t0
+
+
+CPU_NOTE = ("dense C restatement of relative_pose_EKF.cpp (oracle/ekf_oracle.c), gcc -O3, OpenMP over filters; "
+            "the reference's own C++ needs Eigen >= 3.4, which is absent, so it cannot be built here")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores, same scenario / noise / parameters.
+    Rank 0 only; the other ranks exit without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import quadrotor_landing_b200 as q
+    from quadrotor_landing_b200 import scenario
+    p = bench_params(q)
+    scn = scenario.generate(p)          # host-only C++ generator inside libqekf (no GPU needed)
+    threads = os.cpu_count() or 1
+    sample = max(32, 32 * threads)
+    streams = cpu_streams(q, scn, sample)
+    for _ in range(args.warmup):
+        cpu_replay(p, scn, streams, threads)
+    times = [cpu_replay(p, scn, streams, threads) for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    rate = sample * scn.T / dt
+    line = {
+        "impl": "reference", "metric": "EKF filter-steps/s (propagate+update)", "value": rate, "unit": "filter-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, scn),
+        "cpu_baseline": {"value": rate, "unit": "filter-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d filters x %d ticks per step; %s" % (sample, scn.T, CPU_NOTE)},
+        "e2e": {"value": rate, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, scn):
+    return {"workload": "Monte-Carlo replay of a 60 s hover-and-descend landing: %d filters per GPU x %d ticks "
+                        "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), single-rate direct-orientation "
+                        "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T),
+            "filters_per_gpu": args.filters, "ticks": int(scn.T), "tag_arrivals": int(scn.M),
+            "precision": "fp64" if args.precision == 64 else "fp32",
+            "l2": "per-filter state (1.1 GB per 1M filters) is far larger than L2 and is re-read every step; the "
+                  "shared clean scenario (0.7 MB) is L2-resident by design",
+            "parallelism": "filters sharded over %d GPU(s), NCCL all-reduce of the statistics" % args.gpus}
+
+
+def run_ours(args):
+    import torch
+    import quadrotor_landing_b200 as q
+    from quadrotor_landing_b200 import _native as nat
+    from quadrotor_landing_b200 import scenario
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    p = bench_params(q)
+    scn = scenario.generate(p)
+    T, M = scn.T, scn.M
+    N = args.filters
+    prec = q.QEKF_FP64 if args.precision == 64 else q.QEKF_FP32
+    noise = bench_noise(q, first_global_id=rank * N)
+    stride = 200                                   # one statistics sample per simulated second
+    nb = T // stride
+
+    b = q.BatchEKF(p, N, device=local, precision=prec)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    b.stats_configure(nb, stride)
+    stats_dev = torch.zeros((nb, q.STAT_DIM), dtype=torch.float64, device=dev)
+
+    # ---- device-resident inputs (the `value` leg) ----
+    d_imu = torch.tensor(scn.imu_clean, device=dev)
+    d_pose = torch.tensor(scn.tag_pose_clean, device=dev)
+    d_stamp = torch.tensor(scn.tag_stamp, device=dev)
+    d_step = torch.tensor(scn.tag_step, dtype=torch.int32, device=dev)
+    d_truth = torch.tensor(scn.truth, device=dev)
+    sh = q.QekfSharedStreams()
+    sh.T, sh.imu_clean, sh.M = T, d_imu.data_ptr(), M
+    sh.tag_step, sh.tag_pose_clean, sh.tag_stamp = d_step.data_ptr(), d_pose.data_ptr(), d_stamp.data_ptr()
+    sh.truth, sh.t_start, sh.on_device = d_truth.data_ptr(), 0.0, 1
+
+    # ---- pinned host inputs (the `e2e` leg) ----
+    h_imu = torch.tensor(scn.imu_clean).pin_memory()
+    h_pose = torch.tensor(scn.tag_pose_clean).pin_memory()
+    h_stamp = torch.tensor(scn.tag_stamp).pin_memory()
+    h_step = torch.tensor(scn.tag_step, dtype=torch.int32).pin_memory()
+    h_truth = torch.tensor(scn.truth).pin_memory()
+    hs = q.QekfSharedStreams()
+    hs.T, hs.imu_clean, hs.M = T, h_imu.data_ptr(), M
+    hs.tag_step, hs.tag_pose_clean, hs.tag_stamp = h_step.data_ptr(), h_pose.data_ptr(), h_stamp.data_ptr()
+    hs.truth, hs.t_start, hs.on_device = h_truth.data_ptr(), 0.0, 0
+    h2d = h_imu.numel() * 8 + h_pose.numel() * 8 + h_stamp.numel() * 8 + h_step.numel() * 4 + h_truth.numel() * 8
+    h_stats = np.zeros((nb, q.STAT_DIM))
+
+    def one_step(shared, host_result):
+        """One pass of the hot path: reset -> fused replay of all T ticks -> statistics (all-reduced at N>1)."""
+        b.reset_filters()
+        b.stats_reset()
+        b.run_monte_carlo_device(shared, noise, 0, T)
+        b.copy_stats_device(stats_dev.data_ptr())
+        if dist is not None:
+            dist.all_reduce(stats_dev)
+        if host_result:
+            h_stats[:] = stats_dev.cpu().numpy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(shared, host_result, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            one_step(shared, host_result)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if host_result:
+            ms = max(ms, wall * 1e3)          # the host-visible time is what a caller of the C ABI sees
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(sh, False)
+    torch.cuda.synchronize()
+    b.step_counts(reset=True)
+    l0 = b.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    # the fused kernel alone (for the roofline): events around the launch only, on its stream
+    k_ms = []
+    ms_total = timed(sh, False, args.steps)
+    launches = b.launch_count - l0
+    n_pred, n_corr = b.step_counts(reset=True)
+    for _ in range(2):
+        b.reset_filters(); b.stats_reset()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        b.run_monte_carlo_device(sh, noise, 0, T)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        k_ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    one_step(hs, True)                              # warm the host path (staging slab allocation)
+    e2e_ms = timed(hs, True, args.steps)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    steps_per_pass = N * T * world
+    value = steps_per_pass / (ms_per_step * 1e-3)
+    e2e_value = steps_per_pass / (e2e_ms / args.steps * 1e-3)
+    # roofline of the dominant kernel (run_kernel): exact executed work / kernel time
+    fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
+    if prec == q.QEKF_FP32:
+        fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
+    pred_per_launch, corr_per_launch = n_pred / args.steps, n_corr / args.steps
+    flops_per_launch = pred_per_launch * fp + corr_per_launch * fc
+    k_t = float(np.mean(k_ms)) * 1e-3
+    peak = nat.measure_fma_peak(local, prec)
+    achieved = flops_per_launch / k_t / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_bytes = N * STATE_BYTES * (1 if prec == q.QEKF_FP64 else 0.5) + h2d
+    line = {
+        "metric": "EKF filter-steps/s (propagate+update)", "value": value, "unit": "filter-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if prec == q.QEKF_FP64 else "f32", "data": "synthetic",
+        "config": workload_config(args, scn),
+        "e2e": {"value": e2e_value, "unit": "filter-steps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(h_stats.nbytes)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64" if prec == q.QEKF_FP64 else "fp32", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "self-measured FMA microbenchmark in this run (qekf_measure_fma_peak); "
+                                    "MEASURED_PEAKS.json has no CUDA-core figure",
+                     "kernel": "run_kernel", "kernel_ms": k_t * 1e3,
+                     "flops_per_filter_step": flops_per_launch / (N * T),
+                     "work": {"prediction_steps": pred_per_launch, "correction_steps": corr_per_launch,
+                              "flops_per_prediction": fp, "flops_per_correction": fc}},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_bytes / k_t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hbm_bytes / k_t / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "stats": {"rmse_pos_m_final": float(np.sqrt(h_stats[-1, 19] / max(h_stats[-1, 16], 1) / 3)),
+                  "mean_nees_final": float(h_stats[-1, 15] / max(h_stats[-1, 16], 1)),
+                  "samples_final": float(h_stats[-1, 16]), "diverged_total": float(h_stats[:, 18].sum())},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = max(32, 32 * threads)
+        streams = cpu_streams(q, scn, sample)
+        cpu_replay(p, scn, streams, threads)
+        reps = [cpu_replay(p, scn, streams, threads) for _ in range(3)]
+        dt = float(np.mean(reps))
+        line["cpu_baseline"] = {"value": sample * T / dt, "unit": "filter-steps/s", "cores": threads, "kind": "port",
+                                "sample": "%d filters x %d ticks of the same workload, %.1f s per replay; %s"
+                                          % (sample, T, dt, CPU_NOTE)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

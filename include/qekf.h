@@ -215,6 +215,19 @@ int qekf_get_stats(qekf_handle *h, double *out /* host [n_bins][QEKF_STAT_DIM] *
  * stream, so that the caller can all-reduce them across GPUs (NCCL) without a host round trip. */
 int qekf_copy_stats_device(qekf_handle *h, void *dst_device);
 
+/* ---- housekeeping for benchmarking ------------------------------------------------------------------- */
+/* Back to the freshly constructed state: every filter uninitialised, cov_pert = cov_init, counters 0. */
+int qekf_reset_filters(qekf_handle *h);
+/* Number of kernels this handle has launched since creation. */
+int64_t qekf_launch_count(const qekf_handle *h);
+/* prediction_step / correction_step calls executed by the fused kernels since creation (or the last
+ * reset): the exact work count behind a filter-steps/s or FLOP/s figure. */
+int qekf_step_counts(qekf_handle *h, int64_t *n_predict, int64_t *n_correct, int reset);
+/* Self-measured FMA peak of the device (independent FMA chains, no memory traffic), in TFLOP/s counting an
+ * FMA as 2 flops.  precision: QEKF_FP64 or QEKF_FP32.  The roofline denominator for this compute-bound path
+ * (MEASURED_PEAKS.json carries no CUDA-core FP64/FP32 figure). */
+int qekf_measure_fma_peak(int device, int precision, double *tflops);
+
 /* ---- synthetic landing scenario (host; no reference equivalent: the reference was fed by Gazebo) ---- */
 /* Hover `hover_s` at z_start, then smooth-step descent to z_end; lateral sway x = ax sin(wx t),
  * y = ay sin(wy t + phase); yaw = amp sin(w t).  The truth is advanced with the filter's own discrete

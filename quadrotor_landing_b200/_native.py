@@ -130,6 +130,7 @@ EXPORTS = [
     "qekf_scenario_default", "qekf_scenario_sizes", "qekf_scenario_generate",
     "qekf_noise_default", "qekf_run_monte_carlo", "qekf_synthesize_streams", "qekf_stats_configure",
     "qekf_stats_reset", "qekf_get_stats", "qekf_copy_stats_device",
+    "qekf_reset_filters", "qekf_launch_count", "qekf_measure_fma_peak", "qekf_step_counts",
 ]
 
 _lib = None
@@ -181,6 +182,11 @@ def lib() -> C.CDLL:
     L.qekf_stats_reset.argtypes = [vp]
     L.qekf_get_stats.argtypes = [vp, dp]
     L.qekf_copy_stats_device.argtypes = [vp, vp]
+    L.qekf_reset_filters.argtypes = [vp]
+    L.qekf_launch_count.argtypes = [vp]
+    L.qekf_launch_count.restype = C.c_int64
+    L.qekf_measure_fma_peak.argtypes = [C.c_int, C.c_int, dp]
+    L.qekf_step_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     _lib = L
     return L
 
@@ -188,6 +194,13 @@ def lib() -> C.CDLL:
 def check(rc: int):
     if rc != 0:
         raise QekfError(rc, lib().qekf_last_error_string().decode("utf-8", "replace"))
+
+
+def measure_fma_peak(device: int = 0, precision: int = QEKF_FP64) -> float:
+    """Self-measured FMA peak of the device in TFLOP/s (FMA = 2 flops)."""
+    v = C.c_double()
+    check(lib().qekf_measure_fma_peak(int(device), int(precision), C.byref(v)))
+    return v.value
 
 
 def default_noise() -> QekfNoiseSpec:

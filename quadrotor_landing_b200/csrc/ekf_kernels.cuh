@@ -31,6 +31,7 @@ template <typename T> struct DeviceState {
     double *pend;    // [8][ld]    latched-but-unconsumed tag pose + stamp
     int32_t *flags;  // [ld]
     int32_t *upds;   // [ld]       upds_since_correction
+    unsigned long long *counts;   // [2] prediction_step / correction_step calls executed (all launches)
     int64_t ld;
     int64_t n;
 };
@@ -229,6 +230,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
     int32_t upds = a.st.upds[i];
     T accel[3] = { a.st.aux[0 * a.st.ld + i], a.st.aux[1 * a.st.ld + i], a.st.aux[2 * a.st.ld + i] };
 
+    uint32_t n_pred = 0, n_corr = 0;
     int32_t m = a.m0;
     int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     int32_t pend_m = -1;     // index of the latched arrival; -1 = latched pose lives in st.pend
@@ -278,7 +280,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
 
         // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
         prediction_step<T, BIAS>(s, P, u, c, accel);
+        ++n_pred;
         if (perform) {
+            ++n_corr;
             Observation<T> obs;
             correction_step<T, BIAS, DIRECT>(s, P, tag, c, obs);
 #pragma unroll
@@ -308,6 +312,15 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
     store_filter<T>(a.st, i, s, P);
     a.st.flags[i] = flags;
     a.st.upds[i] = upds;
+    if (a.st.counts) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
+        atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
+#else
+        a.st.counts[0] += n_pred;
+        a.st.counts[1] += n_corr;
+#endif
+    }
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
 }

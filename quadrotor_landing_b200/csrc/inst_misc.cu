@@ -83,6 +83,30 @@ cudaError_t launch_stats_reduce(const double *acc, double *out, int64_t n, cudaS
     return cudaGetLastError();
 }
 
+template <typename T> __global__ void fma_peak_kernel(T *sink, int iters)
+{
+    T a[16];
+    const T x = T(1.0000001), y = T(1e-9) * (T)threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = T(j) + y;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = M<T>::fma_(a[j], x, y);
+    }
+    T s = T(0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == T(-1)) sink[0] = s;   // never true; keeps the chains alive
+}
+
+template <typename T> cudaError_t launch_fma_peak(T *sink, int iters, unsigned grid, unsigned block, cudaStream_t stream)
+{
+    fma_peak_kernel<T><<<grid, block, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+}
+template cudaError_t launch_fma_peak<double>(double *, int, unsigned, unsigned, cudaStream_t);
+template cudaError_t launch_fma_peak<float>(float *, int, unsigned, unsigned, cudaStream_t);
+
 #define INST_TB(T, B)                                                                                                   \
     template cudaError_t launch_deliver<T, B>(const DeviceState<T> &, const Consts<T> &, const double *, int, int,      \
                                               unsigned, size_t, cudaStream_t);                                         \

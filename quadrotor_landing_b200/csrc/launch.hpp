@@ -32,6 +32,9 @@ template <typename T>
 cudaError_t launch_dump(const RunArgs<T> &a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,
                         double *tag_out, uint8_t *valid_out, double *bias_out, cudaStream_t stream);
 
+// independent FMA chains, no memory traffic: `iters` x 16 FMAs per thread
+template <typename T> cudaError_t launch_fma_peak(T *sink, int iters, unsigned grid, unsigned block, cudaStream_t stream);
+
 // acc [STAT_REPL][n][STAT_DIM] -> out [n][STAT_DIM]
 cudaError_t launch_stats_reduce(const double *acc, double *out, int64_t n, cudaStream_t stream);
 

@@ -51,6 +51,7 @@ struct qekf_handle {
     void *x = nullptr, *P = nullptr, *aux = nullptr;
     double *pend = nullptr;
     int32_t *flags = nullptr, *upds = nullptr;
+    unsigned long long *counts = nullptr;
     // per-tick interface staging
     double *d_tick = nullptr;        // [6 imu][8 tag]
     double *h_tick = nullptr;        // pinned mirror
@@ -75,7 +76,7 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
 {
     DeviceState<T> s;
     s.x = (T *)h->x; s.P = (T *)h->P; s.aux = (T *)h->aux; s.pend = h->pend;
-    s.flags = h->flags; s.upds = h->upds; s.ld = h->ld; s.n = h->n;
+    s.flags = h->flags; s.upds = h->upds; s.counts = h->counts; s.ld = h->ld; s.n = h->n;
     return s;
 }
 
@@ -103,7 +104,8 @@ int free_state(qekf_handle *h)
 {
     cudaFree(h->x); cudaFree(h->P); cudaFree(h->aux); cudaFree(h->pend);
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
-    cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared);
+    cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared); cudaFree(h->counts);
+    h->counts = nullptr;
     h->stats_acc = h->stats_red = nullptr; h->stats_bins = 0; h->d_shared = nullptr; h->d_shared_bytes = 0;
     if (h->h_tick) cudaFreeHost(h->h_tick);
     h->x = h->P = h->aux = nullptr; h->pend = nullptr; h->flags = h->upds = nullptr;
@@ -123,6 +125,8 @@ int alloc_state(qekf_handle *h)
     CUDA_TRY(cudaMalloc(&h->pend, PEND_DIM * ld * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->flags, ld * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&h->upds, ld * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->stream));
     CUDA_TRY(cudaMalloc(&h->d_tick, 16 * sizeof(double)));
     CUDA_TRY(cudaMallocHost(&h->h_tick, 16 * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(h->x, 0, 16 * ld * h->tsize, h->stream));
@@ -783,6 +787,72 @@ int qekf_get_stats(qekf_handle *h, double *out)
     h->launches++;
     CUDA_TRY(cudaMemcpyAsync(out, h->stats_red, (size_t)h->stats_bins * STAT_DIM * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return QEKF_OK;
+}
+
+// ---- housekeeping ----------------------------------------------------------------------------------------
+
+int qekf_reset_filters(qekf_handle *h)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t ld = (size_t)h->ld;
+    CUDA_TRY(cudaMemsetAsync(h->x, 0, 16 * ld * h->tsize, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->aux, 0, AUX_DIM * ld * h->tsize, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->pend, 0, PEND_DIM * ld * sizeof(double), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->flags, 0, ld * sizeof(int32_t), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->upds, 0, ld * sizeof(int32_t), h->stream));
+    return reset_cov(h, true);
+}
+
+int64_t qekf_launch_count(const qekf_handle *h) { return h ? h->launches : 0; }
+
+int qekf_step_counts(qekf_handle *h, int64_t *n_predict, int64_t *n_correct, int reset)
+{
+    if (!h || !n_predict || !n_correct) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    unsigned long long c[2];
+    CUDA_TRY(cudaMemcpy(c, h->counts, sizeof c, cudaMemcpyDeviceToHost));
+    *n_predict = (int64_t)c[0]; *n_correct = (int64_t)c[1];
+    if (reset) CUDA_TRY(cudaMemset(h->counts, 0, sizeof c));
+    return QEKF_OK;
+}
+
+int qekf_measure_fma_peak(int device, int precision, double *tflops)
+{
+    if (!tflops) return fail(QEKF_ERR_BAD_ARG, "output is NULL");
+    if (precision != QEKF_FP64 && precision != QEKF_FP32) return fail(QEKF_ERR_BAD_ARG, "precision must be 64 or 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(QEKF_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    void *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const unsigned block = 256, grid = (unsigned)prop.multiProcessorCount * 8;
+    const int iters = (precision == QEKF_FP64) ? 8192 : 32768;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        if (precision == QEKF_FP64) CUDA_TRY(launch_fma_peak<double>((double *)sink, iters, grid, block, 0));
+        else CUDA_TRY(launch_fma_peak<float>((float *)sink, iters, grid, block, 0));
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16.0 * (double)iters * (double)block * (double)grid;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = best;
     return QEKF_OK;
 }
 

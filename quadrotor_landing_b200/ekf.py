@@ -79,6 +79,19 @@ class BatchEKF:
     def sync(self):
         check(self._L.qekf_sync(self._h))
 
+    def reset_filters(self):
+        check(self._L.qekf_reset_filters(self._h))
+
+    def step_counts(self, reset=False):
+        """(prediction_step calls, correction_step calls) executed by the fused kernels."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self._L.qekf_step_counts(self._h, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.qekf_launch_count(self._h))
+
     # ---- reference per-tick interface (same input for every filter) ----
     def set_imu(self, accel, gyro):
         a, w = _f64(accel), _f64(gyro)

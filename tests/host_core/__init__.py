@@ -135,3 +135,10 @@ def synthesize(scn, noise, first, count):
                     _dp(o_imu), _dp(o_tag), o_val.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(o_bias))
     return dict(imu=o_imu, tag_step=step.copy(), tag_pose=o_tag, tag_stamp=_f64(scn.tag_stamp).copy(), tag_valid=o_val,
                 bias=o_bias)
+
+
+def count_flops(params):
+    """(predict, correct) floating-point operations executed by the product's structured code (FMA = 2)."""
+    out = np.zeros(2)
+    lib().hc_count_flops(C.byref(params), _dp(out))
+    return int(out[0]), int(out[1])

@@ -3,6 +3,8 @@
 // structured arithmetic and the tick sequencer can be checked against the oracle in the CPU-only test
 // tier.  The product library never contains or calls this; on a GPU the same templates run inside
 // run_kernel.
+#include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -11,6 +13,42 @@
 #include "../../quadrotor_landing_b200/csrc/ekf_params.hpp"
 
 using namespace qekf;
+
+// ---- instrumented real type: counts the floating-point operations the structured code executes -------
+// (FMA = 2; add, sub, mul, div, sqrt, rsqrt = 1; sincos = 2; atan2 = 1).  Used to derive the
+// "algorithmic flops per filter-step" that bench.py's roofline uses.
+struct Cnt {
+    double v;
+    static long long flops;
+    Cnt() : v(0) {}
+    Cnt(double x) : v(x) {}
+    Cnt(int x) : v(x) {}
+    explicit operator double() const { return v; }
+};
+long long Cnt::flops = 0;
+inline Cnt operator+(Cnt a, Cnt b) { Cnt::flops += 1; return Cnt(a.v + b.v); }
+inline Cnt operator-(Cnt a, Cnt b) { Cnt::flops += 1; return Cnt(a.v - b.v); }
+inline Cnt operator*(Cnt a, Cnt b) { Cnt::flops += 1; return Cnt(a.v * b.v); }
+inline Cnt operator/(Cnt a, Cnt b) { Cnt::flops += 1; return Cnt(a.v / b.v); }
+inline Cnt operator-(Cnt a) { return Cnt(-a.v); }
+inline Cnt &operator+=(Cnt &a, Cnt b) { Cnt::flops += 1; a.v += b.v; return a; }
+inline Cnt &operator-=(Cnt &a, Cnt b) { Cnt::flops += 1; a.v -= b.v; return a; }
+inline Cnt &operator*=(Cnt &a, Cnt b) { Cnt::flops += 1; a.v *= b.v; return a; }
+inline bool operator<(Cnt a, Cnt b) { return a.v < b.v; }
+inline bool operator>(Cnt a, Cnt b) { return a.v > b.v; }
+inline bool operator<=(Cnt a, Cnt b) { return a.v <= b.v; }
+inline bool operator>=(Cnt a, Cnt b) { return a.v >= b.v; }
+namespace qekf {
+template <> struct M<Cnt> {
+    static Cnt sqrt_(Cnt x) { Cnt::flops += 1; return Cnt(std::sqrt(x.v)); }
+    static Cnt rsqrt_(Cnt x) { Cnt::flops += 1; return Cnt(1.0 / std::sqrt(x.v)); }
+    static void sincos_(Cnt x, Cnt *s, Cnt *c) { Cnt::flops += 2; *s = Cnt(std::sin(x.v)); *c = Cnt(std::cos(x.v)); }
+    static Cnt atan2_(Cnt y, Cnt x) { Cnt::flops += 1; return Cnt(std::atan2(y.v, x.v)); }
+    static Cnt fma_(Cnt a, Cnt b, Cnt c) { Cnt::flops += 2; return Cnt(a.v * b.v + c.v); }
+    static Cnt abs_(Cnt x) { return Cnt(std::fabs(x.v)); }
+    static Cnt min_(Cnt a, Cnt b) { return Cnt(std::fmin(a.v, b.v)); }
+};
+}  // namespace qekf
 
 namespace {
 
@@ -83,7 +121,7 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     RunArgs<T> a;
     std::memset(&a, 0, sizeof a);
     a.st.x = xs.data(); a.st.P = Ps.data(); a.st.aux = as.data(); a.st.pend = pend;
-    a.st.flags = flags; a.st.upds = upds; a.st.ld = N; a.st.n = N;
+    a.st.flags = flags; a.st.upds = upds; a.st.counts = nullptr; a.st.ld = N; a.st.n = N;
     std::memset(&a.in, 0, sizeof a.in);
     a.in.imu = imu; a.in.tag_step = tag_step; a.in.tag_pose = tag_pose; a.in.tag_stamp = tag_stamp;
     a.in.tag_valid = tag_valid; a.in.cs = N; a.in.is = 1; a.in.M = M; a.in.vs = N;
@@ -113,6 +151,40 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
 }
 
 }  // namespace
+
+// flops executed by one prediction_step / one correction_step of the structured product code, on a
+// typical (large-angle-branch) input.  out[0] = predict, out[1] = correct.
+template <bool BIAS, bool DIRECT> static void count_t(const qekf_params *p, double *out)
+{
+    Consts<double> cd = make_consts<double>(*p);
+    Consts<Cnt> c;
+    {   // Consts<Cnt> has the same field order; convert the real-valued fields one by one
+        const double *src = reinterpret_cast<const double *>(&cd);
+        Cnt *dst = reinterpret_cast<Cnt *>(&c);
+        const size_t nreal = offsetof(Consts<double>, n_tags) / sizeof(double);
+        for (size_t i = 0; i < nreal; ++i) dst[i] = Cnt(src[i]);
+        c.n_tags = cd.n_tags; c.upd_per_meas = cd.upd_per_meas; c.limit_measurement_freq = cd.limit_measurement_freq;
+        c.corner_margin_enbl = cd.corner_margin_enbl; c.dynamic_meas_delay = cd.dynamic_meas_delay;
+    }
+    constexpr int N = BIAS ? 15 : 9;
+    Nominal<Cnt> s;
+    PLocal<Cnt, N> P;
+    for (int k = 0; k < 3; ++k) { s.r[k] = Cnt(0.1 * (k + 1)); s.v[k] = Cnt(0.05 * k); s.ab[k] = Cnt(0.01); s.wb[k] = Cnt(0.001); }
+    s.r[2] = Cnt(2.5);
+    s.q[0] = Cnt(0.05); s.q[1] = Cnt(-0.02); s.q[2] = Cnt(0.15); s.q[3] = Cnt(std::sqrt(1 - 0.05 * 0.05 - 0.02 * 0.02 - 0.15 * 0.15));
+    for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) P.st(i, j, Cnt(i == j ? 0.1 : 0.001 * (i + j)));
+    Cnt u[6] = { Cnt(0.1), Cnt(-0.2), Cnt(9.7), Cnt(0.01), Cnt(-0.02), Cnt(0.05) }, acc[3];
+    Cnt::flops = 0;
+    prediction_step<Cnt, BIAS>(s, P, u, c, acc);
+    out[0] = (double)Cnt::flops;
+    // a tag pose close to the prediction
+    Cnt tag[7] = { Cnt(0.05), Cnt(-0.1), Cnt(2.4), Cnt(0.70), Cnt(-0.71), Cnt(0.03), Cnt(0.02) };
+    Observation<Cnt> obs;
+    Cnt::flops = 0;
+    correction_step<Cnt, BIAS, DIRECT>(s, P, tag, c, obs);
+    out[1] = (double)Cnt::flops;
+}
 
 #define HC_DISPATCH(prec, p, CALL)                                                                  \
     do {                                                                                            \
@@ -152,6 +224,15 @@ void hc_run(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_ste
 #define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds)
     HC_DISPATCH(prec, p, C_);
 #undef C_
+}
+
+void hc_count_flops(const qekf_params *p, double *out)
+{
+    const bool b = p->est_bias != 0, d = p->direct_orien_method != 0;
+    if (b && d) count_t<true, true>(p, out);
+    else if (b) count_t<true, false>(p, out);
+    else if (d) count_t<false, true>(p, out);
+    else count_t<false, false>(p, out);
 }
 
 // Monte-Carlo replay: shared clean streams imu [T][6], tag_pose [M][7]; noise generated per filter.
