@@ -183,6 +183,8 @@ def run_ours(args):
     N = args.filters
     prec = q.QEKF_FP64 if args.precision == 64 else q.QEKF_FP32
     noise = bench_noise(q, first_global_id=rank * N)
+    if args.no_private_dropout:
+        noise.rand_dropout_len = 0
     stride = 200                                   # one statistics sample per simulated second
     nb = T // stride
 
@@ -349,6 +351,7 @@ def main():
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-private-dropout", action="store_true", help="diagnostic: drop the per-filter dropout window")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
