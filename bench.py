@@ -191,7 +191,7 @@ def run_ours(args):
     b = q.BatchEKF(p, N, device=local, precision=prec)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
-    b.stats_configure(nb, stride)
+    b.stats_configure(nb, stride if not args.no_stats else 10 ** 9)
     stats_dev = torch.zeros((nb, q.STAT_DIM), dtype=torch.float64, device=dev)
 
     # ---- device-resident inputs (the `value` leg) ----
@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stats", action="store_true", help="diagnostic: never sample statistics")
     ap.add_argument("--no-private-dropout", action="store_true", help="diagnostic: drop the per-filter dropout window")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -130,9 +130,17 @@ template <typename T, bool SYNTH> struct Inputs {
     }
 };
 
-// one statistics sample of one filter after tick k (SYNTH launches: the truth and the true bias are known)
+#ifdef __CUDA_ARCH__
+#define QEKF_COLD __device__ __noinline__
+#else
+#define QEKF_COLD inline
+#endif
+
+// One statistics sample of one filter after tick k (SYNTH launches: the truth and the true bias are known).
+// Deliberately NOT inlined on the device: it runs once per `stride` ticks and must not take part in the
+// register allocation of the hot loop.
 template <typename T, bool BIAS, class PS>
-QEKF_FN void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> &s, PS &P, const double bias[6])
+QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> s, PS P, const double *bias)
 {
     constexpr int N = PS::n;
     constexpr int NP = N * (N + 1) / 2;
@@ -154,10 +162,13 @@ QEKF_FN void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nomin
         for (int c = 0; c < 3; ++c) { e[9 + c] = (T)bias[c] - s.ab[c]; e[12 + c] = (T)bias[3 + c] - s.wb[c]; }
     }
     // save P, factor in place, restore
-    for (int el = 0; el < NP; ++el) a.st.P[el * a.st.ld + i] = P.el(el);
+    T *gp = a.st.P + i;
+#pragma unroll 8
+    for (int el = 0; el < NP; ++el) gp[el * a.st.ld] = P.el(el);
     T nees;
     bool ok = nees_inplace<T>(P, e, nees);
-    for (int el = 0; el < NP; ++el) P.el(el) = a.st.P[el * a.st.ld + i];
+#pragma unroll 8
+    for (int el = 0; el < NP; ++el) P.el(el) = gp[el * a.st.ld];
     double esq = 0;
     bool finite = true;
 #pragma unroll
@@ -218,56 +229,134 @@ QEKF_FN void store_filter(const DeviceState<T> &st, int64_t i, const Nominal<T> 
 // ------------------------------------------------------------------------------------------------
 // fused multi-tick replay
 // ------------------------------------------------------------------------------------------------
-// The per-filter replay loop.  Host-callable so that the CPU-side unit tests (tests/host_core) can run
-// the very same code against the oracle without a GPU; the product only ever calls it from run_kernel.
+// warp votes (the host instantiation is a "warp" of one lane)
+QEKF_FN unsigned warp_ballot(bool pred)
+{
+#ifdef __CUDA_ARCH__
+    return __ballot_sync(0xffffffffu, pred);
+#else
+    return pred ? 1u : 0u;
+#endif
+}
+QEKF_FN unsigned warp_full_mask()
+{
+#ifdef __CUDA_ARCH__
+    return 0xffffffffu;
+#else
+    return 1u;
+#endif
+}
+QEKF_FN int popcount32(unsigned v)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    int c = 0;
+    for (; v; v &= v - 1) ++c;
+    return c;
+#endif
+}
+
+// The per-filter replay loop, one lane per filter.  Host-callable so that the CPU-side unit tests
+// (tests/host_core) can run the very same code against the oracle without a GPU; the product only ever
+// calls it from run_kernel.
+//
+// Time skew: every lane keeps its OWN tick index k.  The correction step costs 2.5x a prediction and fires
+// once per upd_per_meas ticks; lanes whose cadence is out of phase with their warp-mates (a private tag
+// dropout, a rejected detection, a late initialisation) would make the warp execute it almost every tick
+// with a handful of active lanes.  Instead, a lane whose tick would correct while only a minority of the
+// warp wants to holds that tick back (it simply does not execute this iteration) until a strict majority
+// wants to correct, or its patience (upd_per_meas - 1 iterations) runs out.  Held lanes are then served
+// together and stay aligned from there on.  Filters are independent, so executing a filter's tick a few
+// warp iterations later changes nothing in its arithmetic: results are bit-identical to the unskewed loop.
+// `live` = false marks the padding lanes of a ragged last warp (they only take part in the votes).
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, class PS>
-QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
+QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true)
 {
     const Consts<T> &c = a.c;
+    const int64_t i = live ? i_in : 0;
+    const int64_t k_end = a.k0 + a.n_steps;
     Nominal<T> s;
-    load_filter<T>(a.st, i, s, P);
-    int32_t flags = a.st.flags[i];
-    int32_t upds = a.st.upds[i];
-    T accel[3] = { a.st.aux[0 * a.st.ld + i], a.st.aux[1 * a.st.ld + i], a.st.aux[2 * a.st.ld + i] };
+    int32_t flags = 0, upds = 0;
+    T accel[3] = { T(0), T(0), T(0) };
+    Inputs<T, SYNTH> in;
+    double un[6] = { 0, 0, 0, 0, 0, 0 };
+    int64_t k = k_end;                 // padding lanes are born finished
+    if (live) {
+        load_filter<T>(a.st, i, s, P);
+        flags = a.st.flags[i];
+        upds = a.st.upds[i];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
+        in.init(a, i);
+        k = a.k0;
+        in.raw_imu(k, un);             // software prefetch: un always holds the raw sample of tick k
+    }
 
-    uint32_t n_pred = 0, n_corr = 0;
+    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_cexec = 0, n_sexec = 0;
     int32_t m = a.m0;
     int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
-    int32_t pend_m = -1;     // index of the latched arrival; -1 = latched pose lives in st.pend
+    int32_t pend_m = -1;               // index of the latched arrival; -1 = latched pose lives in st.pend
+    int32_t held = 0;                  // iterations this lane has held its correction tick back
+    bool at_fence = false;             // finished a sampling tick; waiting for the warp to catch up
+    const bool do_stats = SYNTH && a.stats.acc != nullptr;
+    const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
 
-    Inputs<T, SYNTH> in;
-    in.init(a, i);
+    for (;;) {
+        // ---- statistics fence: a lane that has finished a sampling tick waits until every lane of the warp
+        // has, then all sample together (one execution of the sampling code per stride, and the lanes'
+        // time skew is back to zero) ----
+        if (do_stats) {
+            const unsigned fmask = warp_ballot(at_fence || k >= k_end);
+            if (fmask == warp_full_mask() && warp_ballot(at_fence) != 0u) {
+                if (at_fence && (flags & FLAG_INIT)) {
+                    stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias);
+                    ++n_sexec;
+                }
+                at_fence = false;
+            }
+        }
+        const bool active = (k < k_end) && !at_fence;
+        const unsigned amask = warp_ballot(active);
+        if (amask == 0u) {
+            if (do_stats && warp_ballot(at_fence) != 0u) continue;   // only fenced lanes left: sample next turn
+            break;
+        }
+        ++n_iter;
 
-    // software prefetch of the next tick's IMU sample
-    double un[6];
-    in.raw_imu(a.k0, un);
-
-    for (int64_t k = a.k0; k < a.k0 + a.n_steps; ++k) {
-        T u[6];
-        in.imu(k, un, u);
-        if (k + 1 < a.k0 + a.n_steps) in.raw_imu(k + 1, un);
-
-        // ---- AprilTagSubCallback for the arrival scheduled at this tick (node.cpp:153-176) ----
-        if (k == next_tag_step) {
+        // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176); idempotent ----
+        if (active && k == next_tag_step) {
             if (in.valid(m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
-                    T tag[7];
-                    in.tag(m, tag);
-                    initialize_state<T, BIAS>(s, P, tag, c, false);
+                    T tag0[7];
+                    in.tag(m, tag0);
+                    initialize_state<T, BIAS>(s, P, tag0, c, false);
                     flags |= FLAG_INIT;
                 }
             }
             ++m;
             next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
         }
-        if (!(flags & FLAG_INIT)) continue;     // filter_update returns early (cpp:129-130)
 
-        // ---- measurement gating (cpp:147-186) ----
+        // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
+        const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
+                          (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
+        const unsigned wmask = warp_ballot(want);
+        bool serve = true;
+        if (wmask != 0u) {
+            const bool majority = 2 * popcount32(wmask) > popcount32(amask);
+            const bool out_of_patience = warp_ballot(want && held >= patience) != 0u;
+            serve = majority || out_of_patience;
+        }
+        if (want && !serve) ++held;                      // hold tick k back; nothing has been consumed
+        const bool exec = active && !(want && !serve) && (flags & FLAG_INIT);
+
+        // ---- consume the measurement, corner-margin gate (cpp:150-186) ----
         bool perform = false;
         T tag[7];
-        if ((flags & FLAG_READY) && (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas)) {
+        if (exec && want) {
             if (pend_m >= 0) {
                 in.tag(pend_m, tag);
             } else {
@@ -276,30 +365,39 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
             }
             flags &= ~FLAG_READY;
             perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
+            held = 0;
         }
+        if (warp_ballot(perform) != 0u) ++n_cexec;
 
-        // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
-        prediction_step<T, BIAS>(s, P, u, c, accel);
-        ++n_pred;
-        if (perform) {
-            ++n_corr;
-            Observation<T> obs;
-            correction_step<T, BIAS, DIRECT>(s, P, tag, c, obs);
+        if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
+            // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
+            T u[6];
+            in.imu(k, un, u);
+            prediction_step<T, BIAS>(s, P, u, c, accel);
+            ++n_pred;
+            if (perform) {
+                ++n_corr;
+                Observation<T> obs;
+                correction_step<T, BIAS, DIRECT>(s, P, tag, c, obs);
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
+                for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
-            upds = 0;
-            flags |= FLAG_CORRECTED;
-        } else {
-            upds += 1;
-            flags &= ~FLAG_CORRECTED;
+                for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
+                upds = 0;
+                flags |= FLAG_CORRECTED;
+            } else {
+                upds += 1;
+                flags &= ~FLAG_CORRECTED;
+            }
+            flags |= FLAG_ACTIVE;
         }
-        flags |= FLAG_ACTIVE;
-        if (SYNTH) {
-            if (a.stats.acc && ((k + 1) % a.stats.stride) == 0) stats_sample<T, BIAS>(a, i, k, s, P, in.bias);
+        if (active && !(want && !serve)) {
+            ++k;
+            if (k < k_end) in.raw_imu(k, un);
+            if (do_stats && (k % a.stats.stride) == 0) at_fence = true;   // tick k-1 was a sampling tick
         }
     }
+    if (!live) return;
 
     // a latched, still unconsumed measurement survives the launch in st.pend
     if ((flags & FLAG_READY) && pend_m >= 0) {
@@ -316,6 +414,11 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i, PS &P)
 #ifdef __CUDA_ARCH__
         atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
         atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
+        if ((i & 31) == 0) {   // per-warp diagnostics: loop iterations, iterations that ran the correction code
+            atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);
+            atomicAdd(a.st.counts + 3, (unsigned long long)n_cexec);
+        }
+        atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
 #else
         a.st.counts[0] += n_pred;
         a.st.counts[1] += n_corr;
@@ -333,9 +436,8 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= a.st.n) return;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
-    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P);
+    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P, i < a.st.n);   // padding lanes still take part in the warp votes
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -160,29 +160,36 @@ QEKF_FN void stat_add(double *addr, double v)
 #endif
 }
 
-// NEES = e^T P^-1 e by an in-place packed Cholesky P = U^T U carried out IN the covariance storage.
-// The caller must have saved P elsewhere and must restore it afterwards.  Runtime loops on purpose: this
-// runs once every `stride` ticks and must not bloat the instruction footprint of the hot loop.
+// NEES = e^T P^-1 e by an in-place packed Cholesky P = U^T U carried out IN the covariance storage (row j
+// of U overwrites row j of P), with e carried along as an extra right-hand-side column.  The caller must
+// have saved P elsewhere and must restore it afterwards.  The outer (row) loop and the dot products over
+// earlier rows are unrolled so that e / y and the current column stay in registers; the loop over the
+// remaining columns of a row stays a runtime loop to keep the code small (this runs once per `stride` ticks).
 template <typename T, class PS> QEKF_FN bool nees_inplace(PS &P, const T *e, T &nees)
 {
     constexpr int N = PS::n;
     T y[N];
     nees = T(0);
     bool ok = true;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
+        T col[N];                       // U(0..j-1, j): the part of column j above the diagonal
         T d = P.ld(j, j);
         T yj = e[j];
+#pragma unroll
         for (int k = 0; k < j; ++k) {
-            const T ukj = P.ld(k, j);
-            d = M<T>::fma_(-ukj, ukj, d);
-            yj = M<T>::fma_(-ukj, y[k], yj);
+            col[k] = P.ld(k, j);
+            d = M<T>::fma_(-col[k], col[k], d);
+            yj = M<T>::fma_(-col[k], y[k], yj);
         }
-        if (!(d > T(0))) { ok = false; break; }
-        const T inv = T(1) / M<T>::sqrt_(d);
+        ok = ok && (d > T(0));
+        const T inv = M<T>::rsqrt_(ok ? d : T(1));
         P.st(j, j, d * inv);
+#pragma unroll 1
         for (int i = j + 1; i < N; ++i) {
             T v = P.ld(j, i);
-            for (int k = 0; k < j; ++k) v = M<T>::fma_(-P.ld(k, j), P.ld(k, i), v);
+#pragma unroll
+            for (int k = 0; k < j; ++k) v = M<T>::fma_(-col[k], P.ld(k, i), v);
             P.st(j, i, v * inv);
         }
         y[j] = yj * inv;

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -125,8 +126,8 @@ int alloc_state(qekf_handle *h)
     CUDA_TRY(cudaMalloc(&h->pend, PEND_DIM * ld * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->flags, ld * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&h->upds, ld * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(cudaMalloc(&h->counts, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(h->counts, 0, 8 * sizeof(unsigned long long), h->stream));
     CUDA_TRY(cudaMalloc(&h->d_tick, 16 * sizeof(double)));
     CUDA_TRY(cudaMallocHost(&h->h_tick, 16 * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(h->x, 0, 16 * ld * h->tsize, h->stream));
@@ -812,9 +813,12 @@ int qekf_step_counts(qekf_handle *h, int64_t *n_predict, int64_t *n_correct, int
     if (!h || !n_predict || !n_correct) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    unsigned long long c[2];
+    unsigned long long c[8];
     CUDA_TRY(cudaMemcpy(c, h->counts, sizeof c, cudaMemcpyDeviceToHost));
     *n_predict = (int64_t)c[0]; *n_correct = (int64_t)c[1];
+    if (getenv("QEKF_DIAG"))
+        fprintf(stderr, "[qekf diag] predicts %llu corrects %llu | warp iterations %llu, with correction code %llu | stat samples %llu\n",
+                c[0], c[1], c[2], c[3], c[4]);
     if (reset) CUDA_TRY(cudaMemset(h->counts, 0, sizeof c));
     return QEKF_OK;
 }
