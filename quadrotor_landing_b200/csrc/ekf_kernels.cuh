@@ -229,32 +229,68 @@ QEKF_FN void store_filter(const DeviceState<T> &st, int64_t i, const Nominal<T> 
 // ------------------------------------------------------------------------------------------------
 // fused multi-tick replay
 // ------------------------------------------------------------------------------------------------
-// warp votes (the host instantiation is a "warp" of one lane)
-QEKF_FN unsigned warp_ballot(bool pred)
+// correction_step behind a real call on the device: it runs on one tick in upd_per_meas, and keeping it out
+// of line keeps its ~120 live doubles out of the register allocation of the per-tick prediction loop.
+template <typename T, bool BIAS, bool DIRECT, class PS>
+QEKF_COLD void correction_call(Nominal<T> *sp, PS &P, const T *tag, const Consts<T> *c, Observation<T> *obs)
+{
+    Nominal<T> s = *sp;
+    T tg[7];
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) tg[cc] = tag[cc];
+    Observation<T> o;
+    correction_step<T, BIAS, DIRECT>(s, P, tg, *c, o);
+    *sp = s;
+    *obs = o;
+}
+
+// CTA-wide votes, one barrier per loop iteration.  Each warp reduces its lanes with a ballot, lane 0 adds the
+// packed counts into a triple-buffered shared-memory slot, one __syncthreads(), everybody reads.  The barrier
+// also keeps the warps of the CTA walking through the same stretch of the (large, fully unrolled) instruction
+// stream together, so they share its instruction-cache lines.  The host instantiation is a CTA of one lane.
+struct CtaVote {
+    int active, want, fenced, at_fence, lanes;
+    bool out_of_patience;
+};
+constexpr int VOTE_WORDS = 12;   // 3 buffers x 4 words
+
+QEKF_FN void cta_vote_init(int *vbuf)
 {
 #ifdef __CUDA_ARCH__
-    return __ballot_sync(0xffffffffu, pred);
+    if (threadIdx.x < VOTE_WORDS) vbuf[threadIdx.x] = 0;
+    __syncthreads();
 #else
-    return pred ? 1u : 0u;
+    (void)vbuf;
 #endif
 }
-QEKF_FN unsigned warp_full_mask()
+
+QEKF_FN CtaVote cta_vote(int *vbuf, uint32_t iter, bool active, bool want, bool oop, bool fenced, bool at_fence)
 {
+    CtaVote r;
 #ifdef __CUDA_ARCH__
-    return 0xffffffffu;
+    const unsigned full = 0xffffffffu;
+    const unsigned ma = __ballot_sync(full, active), mw = __ballot_sync(full, want), mo = __ballot_sync(full, oop);
+    const unsigned mf = __ballot_sync(full, fenced), mt = __ballot_sync(full, at_fence);
+    int *v = vbuf + (iter % 3u) * 4;
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(v + 0, __popc(ma) | (__popc(mw) << 16));
+        atomicAdd(v + 1, __popc(mf) | (__popc(mt) << 16));
+        if (mo) atomicOr(v + 2, 1);
+    }
+    __syncthreads();
+    const int x0 = v[0], x1 = v[1], x2 = v[2];
+    if (threadIdx.x == 0) {          // recycle the buffer of two iterations ahead (read last in iteration iter-1)
+        int *z = vbuf + ((iter + 2u) % 3u) * 4;
+        z[0] = 0; z[1] = 0; z[2] = 0;
+    }
+    r.active = x0 & 0xffff; r.want = x0 >> 16; r.fenced = x1 & 0xffff; r.at_fence = x1 >> 16;
+    r.out_of_patience = x2 != 0;
+    r.lanes = (int)blockDim.x;
 #else
-    return 1u;
+    (void)vbuf; (void)iter;
+    r.active = active; r.want = want; r.fenced = fenced; r.at_fence = at_fence; r.out_of_patience = oop; r.lanes = 1;
 #endif
-}
-QEKF_FN int popcount32(unsigned v)
-{
-#ifdef __CUDA_ARCH__
-    return __popc(v);
-#else
-    int c = 0;
-    for (; v; v &= v - 1) ++c;
-    return c;
-#endif
+    return r;
 }
 
 // The per-filter replay loop, one lane per filter.  Host-callable so that the CPU-side unit tests
@@ -262,16 +298,18 @@ QEKF_FN int popcount32(unsigned v)
 // calls it from run_kernel.
 //
 // Time skew: every lane keeps its OWN tick index k.  The correction step costs 2.5x a prediction and fires
-// once per upd_per_meas ticks; lanes whose cadence is out of phase with their warp-mates (a private tag
-// dropout, a rejected detection, a late initialisation) would make the warp execute it almost every tick
+// once per upd_per_meas ticks; lanes whose cadence is out of phase with their CTA-mates (a private tag
+// dropout, a rejected detection, a late initialisation) would make the warps execute it almost every tick
 // with a handful of active lanes.  Instead, a lane whose tick would correct while only a minority of the
-// warp wants to holds that tick back (it simply does not execute this iteration) until a strict majority
+// CTA wants to holds that tick back (it simply does not execute this iteration) until a strict majority
 // wants to correct, or its patience (upd_per_meas - 1 iterations) runs out.  Held lanes are then served
 // together and stay aligned from there on.  Filters are independent, so executing a filter's tick a few
-// warp iterations later changes nothing in its arithmetic: results are bit-identical to the unskewed loop.
-// `live` = false marks the padding lanes of a ragged last warp (they only take part in the votes).
+// iterations later changes nothing in its arithmetic: results are bit-identical to the unskewed loop.
+// Statistics fence: a lane that has finished a sampling tick waits until every lane of the CTA has, then all
+// sample together (one execution of the sampling code per stride; the time skew is back to zero).
+// `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, class PS>
-QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true)
+QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
@@ -302,27 +340,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
 
-    for (;;) {
-        // ---- statistics fence: a lane that has finished a sampling tick waits until every lane of the warp
-        // has, then all sample together (one execution of the sampling code per stride, and the lanes'
-        // time skew is back to zero) ----
-        if (do_stats) {
-            const unsigned fmask = warp_ballot(at_fence || k >= k_end);
-            if (fmask == warp_full_mask() && warp_ballot(at_fence) != 0u) {
-                if (at_fence && (flags & FLAG_INIT)) {
-                    stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias);
-                    ++n_sexec;
-                }
-                at_fence = false;
-            }
-        }
+    cta_vote_init(vbuf);
+    for (uint32_t iter = 0;; ++iter) {
         const bool active = (k < k_end) && !at_fence;
-        const unsigned amask = warp_ballot(active);
-        if (amask == 0u) {
-            if (do_stats && warp_ballot(at_fence) != 0u) continue;   // only fenced lanes left: sample next turn
-            break;
-        }
-        ++n_iter;
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176); idempotent ----
         if (active && k == next_tag_step) {
@@ -343,13 +363,19 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const unsigned wmask = warp_ballot(want);
-        bool serve = true;
-        if (wmask != 0u) {
-            const bool majority = 2 * popcount32(wmask) > popcount32(amask);
-            const bool out_of_patience = warp_ballot(want && held >= patience) != 0u;
-            serve = majority || out_of_patience;
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;     // every lane of the CTA has finished
+        ++n_iter;
+        if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
+            // every lane is at the fence (or finished): sample together, then resume on the next iteration
+            if (at_fence && (flags & FLAG_INIT)) {
+                stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias);
+                ++n_sexec;
+            }
+            at_fence = false;
         }
+        bool serve = true;
+        if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
         if (want && !serve) ++held;                      // hold tick k back; nothing has been consumed
         const bool exec = active && !(want && !serve) && (flags & FLAG_INIT);
 
@@ -367,7 +393,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
             perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
             held = 0;
         }
-        if (warp_ballot(perform) != 0u) ++n_cexec;
+        if (perform) ++n_cexec;
 
         if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
             // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
@@ -378,7 +404,11 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
             if (perform) {
                 ++n_corr;
                 Observation<T> obs;
-                correction_step<T, BIAS, DIRECT>(s, P, tag, c, obs);
+                {
+                    Nominal<T> tmp = s;
+                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, &c, &obs);
+                    s = tmp;
+                }
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
@@ -414,10 +444,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 #ifdef __CUDA_ARCH__
         atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
         atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
-        if ((i & 31) == 0) {   // per-warp diagnostics: loop iterations, iterations that ran the correction code
-            atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);
-            atomicAdd(a.st.counts + 3, (unsigned long long)n_cexec);
-        }
+        if ((i & 31) == 0) atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);   // loop iterations per warp
         atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
 #else
         a.st.counts[0] += n_pred;
@@ -437,7 +464,8 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
-    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P, i < a.st.n);   // padding lanes still take part in the warp votes
+    int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
+    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P, i < a.st.n, vbuf);   // padding lanes still take part in the votes
 }
 
 // ------------------------------------------------------------------------------------------------

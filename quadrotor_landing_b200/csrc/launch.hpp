@@ -8,7 +8,7 @@
 
 namespace qekf {
 
-constexpr int BLOCK = 32;   // one warp per CTA: no intra-CTA synchronisation is ever needed
+constexpr int BLOCK = 224;  // 7 warps: 7 x 30 KB of FP64 covariance fill one SM's shared memory (1 CTA / SM)
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);

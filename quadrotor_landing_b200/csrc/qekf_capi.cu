@@ -81,7 +81,7 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     return s;
 }
 
-size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize; }
+size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize + VOTE_WORDS * sizeof(int); }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
 
 // dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision
@@ -817,8 +817,7 @@ int qekf_step_counts(qekf_handle *h, int64_t *n_predict, int64_t *n_correct, int
     CUDA_TRY(cudaMemcpy(c, h->counts, sizeof c, cudaMemcpyDeviceToHost));
     *n_predict = (int64_t)c[0]; *n_correct = (int64_t)c[1];
     if (getenv("QEKF_DIAG"))
-        fprintf(stderr, "[qekf diag] predicts %llu corrects %llu | warp iterations %llu, with correction code %llu | stat samples %llu\n",
-                c[0], c[1], c[2], c[3], c[4]);
+        fprintf(stderr, "[qekf diag] predicts %llu corrects %llu | warp iterations %llu | stat samples %llu\n", c[0], c[1], c[2], c[4]);
     if (reset) CUDA_TRY(cudaMemset(h->counts, 0, sizeof c));
     return QEKF_OK;
 }
