@@ -24,8 +24,9 @@ def _units():
     for t in ("double", "float"):
         for b in (1, 0):
             for d in (1, 0):
-                units.append(("inst_run_%s_b%d_d%d" % (t, b, d), "inst_run.cu",
-                              ["-DQ_T=%s" % t, "-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d]))
+                for m in (0, 1):
+                    units.append(("inst_run_%s_b%d_d%d_m%d" % (t, b, d, m), "inst_run.cu",
+                                  ["-DQ_T=%s" % t, "-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d, "-DQ_MR=%d" % m]))
     return units
 
 

@@ -74,7 +74,8 @@ template <typename T> struct Consts {
     T tag_hw[16];         // tag_widths/2
     T tag_px[16], tag_py[16];
     T small_ang_tol;
-    T meas_delay, meas_delay_max, dyn_offset;
+    double meas_delay, meas_delay_max, dyn_offset;   // seconds; the delay -> step rounding is done in double (cpp:199-200)
+    double dT_nom;        // 1/update_freq in double, for the same reason
     int n_tags;
     int upd_per_meas;     // ceil(update_freq/measurement_freq)           (cpp:91)
     int limit_measurement_freq, corner_margin_enbl, dynamic_meas_delay;
@@ -83,6 +84,44 @@ template <typename T> struct Consts {
 // Nominal state of one filter: x = [r v q(xyzw) ab wb]  (relative_pose_EKF.cpp:244-245)
 template <typename T> struct Nominal {
     T r[3], v[3], q[4], ab[3], wb[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// parameter views.  The step functions read the parameters a sweep may override per filter (Q, R and the
+// camera extrinsic, BASELINE config 5) through a view: ParU serves them from the launch-wide constant
+// block, ParF from this filter's column of a [PF_DIM][ld] table in global memory (derived quantities
+// included, so the kernel does no per-filter parameter derivation).  Everything else comes from view.c.
+// ------------------------------------------------------------------------------------------------
+enum { PF_Q = 0, PF_RA = 12, PF_RC = 15, PF_RAS = 21, PF_D = 27, PF_CVC = 36, PF_RVCV = 45, PF_QVC = 48, PF_DIM = 52 };
+
+template <typename T> struct ParU {
+    const Consts<T> &c;
+    QEKF_FN T Q(int i) const { return c.Q[i]; }
+    QEKF_FN T Ra(int i) const { return c.Ra[i]; }
+    QEKF_FN T RC(int i) const { return c.RC[i]; }
+    QEKF_FN T RA(int i) const { return c.RA[i]; }
+    QEKF_FN T D(int i) const { return c.D[i]; }
+    QEKF_FN T C_vc(int i) const { return c.C_vc[i]; }
+    QEKF_FN T r_v_cv(int i) const { return c.r_v_cv[i]; }
+    QEKF_FN T q_vc(int i) const { return c.q_vc[i]; }
+    QEKF_FN double meas_delay() const { return c.meas_delay; }
+    QEKF_FN double dyn_offset() const { return c.dyn_offset; }
+};
+template <typename T> struct ParF {
+    const Consts<T> &c;
+    const T *t;          // this filter's column of the [PF_DIM][ld] table
+    const double *dl;    // this filter's column of the [2][ld] delay table (measurement_delay, dyn offset)
+    int64_t ld;
+    QEKF_FN T Q(int i) const { return t[(PF_Q + i) * ld]; }
+    QEKF_FN T Ra(int i) const { return t[(PF_RA + i) * ld]; }
+    QEKF_FN T RC(int i) const { return t[(PF_RC + i) * ld]; }
+    QEKF_FN T RA(int i) const { return t[(PF_RAS + i) * ld]; }
+    QEKF_FN T D(int i) const { return t[(PF_D + i) * ld]; }
+    QEKF_FN T C_vc(int i) const { return t[(PF_CVC + i) * ld]; }
+    QEKF_FN T r_v_cv(int i) const { return t[(PF_RVCV + i) * ld]; }
+    QEKF_FN T q_vc(int i) const { return t[(PF_QVC + i) * ld]; }
+    QEKF_FN double meas_delay() const { return dl[0]; }
+    QEKF_FN double dyn_offset() const { return dl[ld]; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -260,19 +299,24 @@ template <typename T> QEKF_FN void quat_log(const T q[4], T v[3])
 // ------------------------------------------------------------------------------------------------
 // initialize_state                                              relative_pose_EKF.cpp:305-344
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool BIAS, class PS>
-QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const Consts<T> &c,
-                                                 bool reinit_bias)
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const PAR &par, bool reinit_bias)
 {
-    T qq[4];
-    quat_mul(c.q_vc, tag + 3, qq);
+    const Consts<T> &c = par.c;
+    T qq[4], Cvc[9];
+    {
+        T qvc[4] = { par.q_vc(0), par.q_vc(1), par.q_vc(2), par.q_vc(3) };
+        quat_mul(qvc, tag + 3, qq);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Cvc[i] = par.C_vc(i);
     s.q[0] = -qq[0]; s.q[1] = -qq[1]; s.q[2] = -qq[2]; s.q[3] = qq[3];
     quat_normclip(s.q);
     T Rq[9], pc[3], ro[3];
     quat_to_rot(s.q, Rq);
-    mv(c.C_vc, tag, pc);
+    mv(Cvc, tag, pc);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) pc[i] += c.r_v_cv[i];
+    for (int i = 0; i < 3; ++i) pc[i] += par.r_v_cv(i);
     mv(Rq, pc, ro);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { s.r[i] = -ro[i]; s.v[i] = T(0); }
@@ -294,9 +338,10 @@ QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const Consts
 // (A = -dT C skew(a), B = -dT C, Phi = F_theta_theta), so  F P F^T  is three in-place symmetric
 // congruences, each touching one block row/column.  W Q W^T = blockdiag(0, C Qa C^T, Qw, Qab, Qwb).
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool BIAS, class PS>
-QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const Consts<T> &c, T accel[3])
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par, T accel[3])
 {
+    const Consts<T> &c = par.c;
     const T d = c.dT;
     T A[9], B[9], Phi[9], QV[6];
     {
@@ -334,8 +379,8 @@ QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const Consts<T>
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = i; j < 3; ++j) {
-                    QV[e++] = C[i * 3 + 0] * c.Q[0] * C[j * 3 + 0] + C[i * 3 + 1] * c.Q[1] * C[j * 3 + 1] +
-                              C[i * 3 + 2] * c.Q[2] * C[j * 3 + 2];
+                    QV[e++] = C[i * 3 + 0] * par.Q(0) * C[j * 3 + 0] + C[i * 3 + 1] * par.Q(1) * C[j * 3 + 1] +
+                              C[i * 3 + 2] * par.Q(2) * C[j * 3 + 2];
                 }
         }
         // attitude: q <- normclip(q (x) exp(dT w)); Phi = I - skew(dT w) or Rodrigues(-|dT w|)
@@ -509,15 +554,15 @@ QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const Consts<T>
             }
             mm_acc(m, Phi, thth);       // m = Phi (th,th) - dT (wb,th)_old
             mmt_acc(n, m, Phi);         // n = m Phi^T - dT (th,wb)_new
-            n[0] += c.Q[3]; n[4] += c.Q[4]; n[8] += c.Q[5];
+            n[0] += par.Q(3); n[4] += par.Q(4); n[8] += par.Q(5);
             stb(P, BTH, BTH, n);
             if (BIAS) stb(P, BTH, BWB, thw_n);
         }
         if (BIAS) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                P.st(9 + i, 9 + i, P.ld(9 + i, 9 + i) + c.Q[6 + i]);
-                P.st(12 + i, 12 + i, P.ld(12 + i, 12 + i) + c.Q[9 + i]);
+                P.st(9 + i, 9 + i, P.ld(9 + i, 9 + i) + par.Q(6 + i));
+                P.st(12 + i, 12 + i, P.ld(12 + i, 12 + i) + par.Q(9 + i));
             }
         }
     }
@@ -588,9 +633,8 @@ template <typename T> struct Observation {
 // i.e. exactly  P^ = (I - K G) P  and  dx = K dy  without materialising K or I - K G.
 // JOSEPH selects the symmetrised Joseph form used by the FP32 mode.
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool BIAS, bool DIRECT, class PS>
-QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<T> &c,
-                                                Observation<T> &obs)
+template <typename T, bool BIAS, bool DIRECT, class PS, class PAR>
+QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &par, Observation<T> &obs)
 {
     constexpr int NB = BIAS ? 5 : 3;
     T dy[6];
@@ -601,16 +645,18 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<
         T C[9];
         quat_to_rot(s.q, C);
         {
-            T qq[4];
-            quat_mul(c.q_vc, tag + 3, qq);
+            T qq[4], qvc[4] = { par.q_vc(0), par.q_vc(1), par.q_vc(2), par.q_vc(3) };
+            quat_mul(qvc, tag + 3, qq);
             obs.q_tv_obs[0] = -qq[0]; obs.q_tv_obs[1] = -qq[1]; obs.q_tv_obs[2] = -qq[2]; obs.q_tv_obs[3] = qq[3];
             quat_normclip(obs.q_tv_obs);
         }
         {
-            T pc[3], ro[3];
-            mv(c.C_vc, tag, pc);
+            T pc[3], ro[3], Cvc[9];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) pc[i] += c.r_v_cv[i];
+            for (int i = 0; i < 9; ++i) Cvc[i] = par.C_vc(i);
+            mv(Cvc, tag, pc);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pc[i] += par.r_v_cv(i);
             if (DIRECT) {
                 T Ro[9];
                 quat_to_rot(obs.q_tv_obs, Ro);
@@ -631,7 +677,8 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<
         T Rk[21];
         {
             // (0,0) block: C RC C^T  (+ skew(r) diag(Ra) skew(r)^T for the direct model)
-            T RCf[9] = { c.RC[0], c.RC[1], c.RC[2], c.RC[1], c.RC[3], c.RC[4], c.RC[2], c.RC[4], c.RC[5] };
+            const T rc1 = par.RC(1), rc2 = par.RC(2), rc4 = par.RC(4);
+            T RCf[9] = { par.RC(0), rc1, rc2, rc1, par.RC(3), rc4, rc2, rc4, par.RC(5) };
             T t[9], r00[9];
             mm_set(t, C, RCf);
 #pragma unroll
@@ -639,7 +686,7 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<
             mmt_acc(r00, t, C);
             if (DIRECT) {
                 const T rx = s.r[0], ry = s.r[1], rz = s.r[2];
-                const T a0 = c.Ra[0], a1 = c.Ra[1], a2 = c.Ra[2];
+                const T a0 = par.Ra(0), a1 = par.Ra(1), a2 = par.Ra(2);
                 // skew(r) diag(a) skew(r)^T
                 r00[0] += a1 * rz * rz + a2 * ry * ry;
                 r00[1] += -a2 * rx * ry;
@@ -650,9 +697,10 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<
                 // (0,1) block: skew(r) D
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    Rk[sym_idx<6>(0, 3 + j)] = -rz * c.D[3 + j] + ry * c.D[6 + j];
-                    Rk[sym_idx<6>(1, 3 + j)] = rz * c.D[0 + j] - rx * c.D[6 + j];
-                    Rk[sym_idx<6>(2, 3 + j)] = -ry * c.D[0 + j] + rx * c.D[3 + j];
+                    const T d0 = par.D(0 + j), d1 = par.D(3 + j), d2 = par.D(6 + j);
+                    Rk[sym_idx<6>(0, 3 + j)] = -rz * d1 + ry * d2;
+                    Rk[sym_idx<6>(1, 3 + j)] = rz * d0 - rx * d2;
+                    Rk[sym_idx<6>(2, 3 + j)] = -ry * d0 + rx * d1;
                 }
             } else {
 #pragma unroll
@@ -662,8 +710,8 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const Consts<
             }
             Rk[sym_idx<6>(0, 0)] = r00[0]; Rk[sym_idx<6>(0, 1)] = r00[1]; Rk[sym_idx<6>(0, 2)] = r00[2];
             Rk[sym_idx<6>(1, 1)] = r00[4]; Rk[sym_idx<6>(1, 2)] = r00[5]; Rk[sym_idx<6>(2, 2)] = r00[8];
-            Rk[sym_idx<6>(3, 3)] = c.RA[0]; Rk[sym_idx<6>(3, 4)] = c.RA[1]; Rk[sym_idx<6>(3, 5)] = c.RA[2];
-            Rk[sym_idx<6>(4, 4)] = c.RA[3]; Rk[sym_idx<6>(4, 5)] = c.RA[4]; Rk[sym_idx<6>(5, 5)] = c.RA[5];
+            Rk[sym_idx<6>(3, 3)] = par.RA(0); Rk[sym_idx<6>(3, 4)] = par.RA(1); Rk[sym_idx<6>(3, 5)] = par.RA(2);
+            Rk[sym_idx<6>(4, 4)] = par.RA(3); Rk[sym_idx<6>(4, 5)] = par.RA(4); Rk[sym_idx<6>(5, 5)] = par.RA(5);
         }
         if (!DIRECT) {
             // Gam = C skew(C^T r)

@@ -34,6 +34,36 @@ template <typename T> struct DeviceState {
     unsigned long long *counts;   // [2] prediction_step / correction_step calls executed (all launches)
     int64_t ld;
     int64_t n;
+    // Delayed-measurement fusion (multirate_ekf, cpp:196-236,251-264): instead of the reference's vectors of
+    // (x, u, P) per tick, a lagged checkpoint (the oldest history entry that can still be addressed) plus a
+    // ring of the IMU inputs of the entries after it.  Every later entry is a pure function of those
+    // (x_hist[i] = prediction_step(x_hist[i-1], u_hist[i])), so it is recomputed when needed.  nullptr when
+    // the handle is single-rate.
+    T *xc;              // [16][ld]   checkpoint nominal state
+    T *Pc;              // [NP][ld]   checkpoint covariance
+    T *ring;            // [ring_len][6][ld]  u_hist of entry e at slot e % ring_len
+    int32_t *nh;        // [ld] history entries after the checkpoint (the head is entry nh)
+    int32_t *hpos;      // [ld] ring slot of the head entry
+    int32_t *hlen;      // [ld] x_hist.size() as the reference would report it (grows without bound between corrections)
+    int32_t ring_len;   // L >= dmax_m1 + 1 + upd_per_meas
+    int32_t dmax_m1;    // D - 1, D = largest step delay any correction of this handle can use
+    // Per-filter parameter overrides (BASELINE config 5); nullptr = launch-wide constants only.
+    const T *pf;              // [PF_DIM][ld]
+    const double *pf_delay;   // [2][ld]
+};
+
+// the parameter view of filter i: launch-wide constants, or this filter's column of the override table
+template <typename T, bool PF> struct ParSel;
+template <typename T> struct ParSel<T, false> {
+    using type = ParU<T>;
+    static QEKF_FN type make(const Consts<T> &c, const DeviceState<T> &, int64_t) { return type{ c }; }
+};
+template <typename T> struct ParSel<T, true> {
+    using type = ParF<T>;
+    static QEKF_FN type make(const Consts<T> &c, const DeviceState<T> &st, int64_t i)
+    {
+        return type{ c, st.pf + i, st.pf_delay + i, st.ld };
+    }
 };
 
 // Input streams as seen by the kernel.  Element (k, c) of filter i lives at base[(k*6+c)*cs + i*is]:
@@ -231,15 +261,15 @@ QEKF_FN void store_filter(const DeviceState<T> &st, int64_t i, const Nominal<T> 
 // ------------------------------------------------------------------------------------------------
 // correction_step behind a real call on the device: it runs on one tick in upd_per_meas, and keeping it out
 // of line keeps its ~120 live doubles out of the register allocation of the per-tick prediction loop.
-template <typename T, bool BIAS, bool DIRECT, class PS>
-QEKF_COLD void correction_call(Nominal<T> *sp, PS &P, const T *tag, const Consts<T> *c, Observation<T> *obs)
+template <typename T, bool BIAS, bool DIRECT, class PS, class PAR>
+QEKF_COLD void correction_call(Nominal<T> *sp, PS &P, const T *tag, const PAR par, Observation<T> *obs)
 {
     Nominal<T> s = *sp;
     T tg[7];
 #pragma unroll
     for (int cc = 0; cc < 7; ++cc) tg[cc] = tag[cc];
     Observation<T> o;
-    correction_step<T, BIAS, DIRECT>(s, P, tg, *c, o);
+    correction_step<T, BIAS, DIRECT>(s, P, tg, par, o);
     *sp = s;
     *obs = o;
 }
@@ -308,11 +338,12 @@ QEKF_FN CtaVote cta_vote(int *vbuf, uint32_t iter, bool active, bool want, bool 
 // Statistics fence: a lane that has finished a sampling tick waits until every lane of the CTA has, then all
 // sample together (one execution of the sampling code per stride; the time skew is back to zero).
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
-template <typename T, bool BIAS, bool DIRECT, bool SYNTH, class PS>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
 QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
+    const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
     const int64_t k_end = a.k0 + a.n_steps;
     Nominal<T> s;
     int32_t flags = 0, upds = 0;
@@ -352,7 +383,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
                 if (!(flags & FLAG_INIT)) {
                     T tag0[7];
                     in.tag(m, tag0);
-                    initialize_state<T, BIAS>(s, P, tag0, c, false);
+                    initialize_state<T, BIAS>(s, P, tag0, par, false);
                     flags |= FLAG_INIT;
                 }
             }
@@ -399,14 +430,14 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
             // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
             T u[6];
             in.imu(k, un, u);
-            prediction_step<T, BIAS>(s, P, u, c, accel);
+            prediction_step<T, BIAS>(s, P, u, par, accel);
             ++n_pred;
             if (perform) {
                 ++n_corr;
                 Observation<T> obs;
                 {
                     Nominal<T> tmp = s;
-                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, &c, &obs);
+                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, par, &obs);
                     s = tmp;
                 }
 #pragma unroll
@@ -455,8 +486,259 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
 }
 
-// fused multi-tick replay (single-rate filter: multirate_ekf = false)
-template <typename T, bool BIAS, bool DIRECT, bool SYNTH, int BLOCK>
+// ------------------------------------------------------------------------------------------------
+// delayed-measurement fusion (multirate_ekf = true), evaluated lazily
+// ------------------------------------------------------------------------------------------------
+template <typename T, class PS>
+QEKF_FN void load_checkpoint(const DeviceState<T> &st, int64_t i, Nominal<T> &s, PS &P)
+{
+    DeviceState<T> v = st;
+    v.x = st.xc; v.P = st.Pc;
+    load_filter<T>(v, i, s, P);
+}
+template <typename T, class PS>
+QEKF_FN void store_checkpoint(const DeviceState<T> &st, int64_t i, const Nominal<T> &s, const PS &P)
+{
+    DeviceState<T> v = st;
+    v.x = st.xc; v.P = st.Pc;
+    store_filter<T>(v, i, s, P);
+}
+
+// n consecutive prediction_steps through the stored IMU inputs of ring slots first, first+1, ... (mod L).
+// One out-of-line copy of the prediction code serves the replay before a delayed correction, the checkpoint
+// catch-up and the materialisation of the head, so the whole multirate tick loop stays small.
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_i, int64_t ld, int32_t L, int32_t first,
+                            int32_t n, T *accel_out)
+{
+    if (n <= 0) return;
+    Nominal<T> s = *sp;
+    T acc[3] = { accel_out[0], accel_out[1], accel_out[2] };
+    int32_t slot = first;
+    T u[6];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) u[cc] = ring_i[((int64_t)slot * 6 + cc) * ld];
+    for (int32_t j = 0; j < n; ++j) {
+        slot = (slot + 1 == L) ? 0 : slot + 1;
+        T un[6];
+        if (j + 1 < n) {                 // software prefetch of the next entry's input
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) un[cc] = ring_i[((int64_t)slot * 6 + cc) * ld];
+        }
+        prediction_step<T, BIAS>(s, P, u, par, acc);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) u[cc] = un[cc];
+    }
+    *sp = s;
+    accel_out[0] = acc[0]; accel_out[1] = acc[1]; accel_out[2] = acc[2];
+}
+
+// The multirate replay loop of one filter.  Semantics: filter_update with multirate_ekf = true
+// (cpp:196-264).  Mechanics: the registers / shared memory hold the CHECKPOINT (oldest retained history
+// entry), not the head.  A tick only appends its IMU sample to the ring (the head prediction of cpp:240-257 is
+// implied, not executed).  A correction with step delay d lands on history entry size-d: the checkpoint is
+// advanced to that entry (ind_rel prediction_steps), corrected there, and becomes the new oldest entry
+// (cpp:206-218); the re-propagation of cpp:222-226 is again implied.  The head is materialised (nh
+// prediction_steps on a copy) only where somebody looks at it: at the end of the launch and at statistics
+// samples.  Every history entry is the same pure function of (checkpoint, ring) the reference evaluates, so
+// the results are bit-identical to the eager evaluation, for ~1 prediction per tick instead of ~2.
+// Ring invariant: nh <= L - 1 before a push and the checkpoint never passes entry size-D (D = largest possible
+// step delay), so every index a future correction can address is still reachable.  Lanes that do not correct
+// (tag dropout, rejected detection) catch their checkpoint up to size-D inside their CTA-mates' correction
+// events, where the warp executes prediction code anyway.
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
+QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
+{
+    const Consts<T> &c = a.c;
+    const int64_t i = live ? i_in : 0;
+    const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
+    const int64_t k_end = a.k0 + a.n_steps;
+    const int32_t L = a.st.ring_len, Dm1 = a.st.dmax_m1;
+    T *ring_i = a.st.ring + i;
+    Nominal<T> s;                      // the checkpoint
+    int32_t flags = 0, upds = 0, nh = 0, hpos = 0, hlen = 0;
+    T accel[3] = { T(0), T(0), T(0) };
+    Inputs<T, SYNTH> in;
+    double un[6] = { 0, 0, 0, 0, 0, 0 };
+    int64_t k = k_end;
+    if (live) {
+        load_checkpoint<T>(a.st, i, s, P);
+        flags = a.st.flags[i];
+        upds = a.st.upds[i];
+        nh = a.st.nh[i]; hpos = a.st.hpos[i]; hlen = a.st.hlen[i];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
+        in.init(a, i);
+        k = a.k0;
+        in.raw_imu(k, un);
+    }
+
+    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0;
+    int32_t m = a.m0;
+    int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+    int32_t pend_m = -1;
+    int32_t held = 0;
+    bool at_fence = false;
+    const bool do_stats = SYNTH && a.stats.acc != nullptr;
+    const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
+
+    cta_vote_init(vbuf);
+    for (uint32_t iter = 0;; ++iter) {
+        const bool active = (k < k_end) && !at_fence;
+
+        // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
+        if (active && k == next_tag_step) {
+            if (in.valid(m, (int32_t)k)) {
+                pend_m = m;
+                flags |= FLAG_READY;
+                if (!(flags & FLAG_INIT)) {
+                    T tag0[7];
+                    in.tag(m, tag0);
+                    initialize_state<T, BIAS>(s, P, tag0, par, false);
+                    flags |= FLAG_INIT;
+                    nh = 0; hlen = 1;                    // history <- single entry (cpp:326-339)
+                }
+            }
+            ++m;
+            next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+        }
+
+        const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
+                          (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;
+        ++n_iter;
+        if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
+            if (at_fence && (flags & FLAG_INIT)) {
+                // look at the head: park the checkpoint, replay the nh implied predictions, sample, come back
+                store_checkpoint<T>(a.st, i, s, P);
+                int32_t first = hpos - nh + 1;
+                if (first < 0) first += L;
+                Nominal<T> head = s;
+                advance_call<T, BIAS>(&head, P, par, ring_i, a.st.ld, L, first, nh, accel);
+                n_pred += (uint32_t)nh;
+                stats_sample<T, BIAS>(a, i, k - 1, head, P, in.bias);
+                load_checkpoint<T>(a.st, i, s, P);
+                ++n_sexec;
+            }
+            at_fence = false;
+        }
+        bool serve = true;
+        if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
+        const bool event = (v.want != 0) && serve;       // CTA-uniform: corrections are being served now
+        if (want && !serve) ++held;
+        const bool exec = active && !(want && !serve) && (flags & FLAG_INIT);
+
+        // ---- consume the measurement, corner-margin gate (cpp:150-186) ----
+        bool perform = false;
+        T tag[7];
+        double stamp = 0;
+        if (exec && want) {
+            if (pend_m >= 0) {
+                in.tag(pend_m, tag);
+                stamp = a.in.tag_stamp[pend_m];
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
+                stamp = a.st.pend[7 * a.st.ld + i];
+            }
+            flags &= ~FLAG_READY;
+            perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
+            held = 0;
+        }
+
+        // ---- how far this lane moves its checkpoint now ----
+        int32_t n_adv = 0;
+        if (perform) {
+            // cpp:199-201
+            const double t_curr = a.in.t_start + (double)k / a.in.update_freq;
+            const double delay = c.dynamic_meas_delay ? fmin(t_curr - stamp + par.dyn_offset(), c.meas_delay_max)
+                                                      : par.meas_delay();
+            int32_t step = (int32_t)(delay / c.dT_nom + 0.5);
+            if (step < 1) step = 1;
+            int32_t ind = hlen - step;
+            if (ind < 0) ind = 0;
+            n_adv = ind - (hlen - 1 - nh);               // >= 0 by the ring invariant
+            if (n_adv < 0) n_adv = 0;
+            a.st.aux[10 * a.st.ld + i] = (T)delay;       // measurement_delay_curr
+        } else if ((flags & FLAG_INIT) && active && (event || (exec && nh >= L - 1))) {
+            n_adv = (nh > Dm1) ? nh - Dm1 : 0;           // catch-up (never past entry size-D)
+        }
+        if (event || n_adv > 0) {
+            int32_t first = hpos - nh + 1;
+            if (first < 0) first += L;
+            T scratch[3] = { T(0), T(0), T(0) };
+            advance_call<T, BIAS>(&s, P, par, ring_i, a.st.ld, L, first, n_adv, scratch);
+            nh -= n_adv;
+            n_pred += (uint32_t)n_adv;
+        }
+        if (perform) {
+            ++n_corr;
+            Observation<T> obs;
+            correction_call<T, BIAS, DIRECT>(&s, P, tag, par, &obs);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
+            hlen = nh + 1;                               // history before the corrected entry is erased (cpp:214-219)
+        }
+        if (exec) {
+            // cpp:240-257: the head prediction is implied; its input joins the history
+            T u[6];
+            in.imu(k, un, u);
+            hpos = (hpos + 1 == L) ? 0 : hpos + 1;
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) ring_i[((int64_t)hpos * 6 + cc) * a.st.ld] = u[cc];
+            ++nh; ++hlen;
+            if (perform) { upds = 0; flags |= FLAG_CORRECTED; }
+            else { upds += 1; flags &= ~FLAG_CORRECTED; }
+            flags |= FLAG_ACTIVE;
+        }
+        if (active && !(want && !serve)) {
+            ++k;
+            if (k < k_end) in.raw_imu(k, un);
+            if (do_stats && (k % a.stats.stride) == 0) at_fence = true;
+        }
+    }
+    if (!live) return;
+
+    if ((flags & FLAG_READY) && pend_m >= 0) {
+        double tg[7];
+        in.tag_f64(pend_m, tg);
+#pragma unroll
+        for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
+        a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
+    }
+    // checkpoint home, then the head (what the accessors read: r_nom ... cov_pert, accel_rel)
+    // (an uninitialised filter keeps the constructor's state: cpp:129-130 returns before touching anything)
+    if (flags & FLAG_INIT) {
+        store_checkpoint<T>(a.st, i, s, P);
+        int32_t first = hpos - nh + 1;
+        if (first < 0) first += L;
+        advance_call<T, BIAS>(&s, P, par, ring_i, a.st.ld, L, first, nh, accel);
+        n_pred += (uint32_t)nh;
+        store_filter<T>(a.st, i, s, P);
+    }
+    a.st.flags[i] = flags;
+    a.st.upds[i] = upds;
+    a.st.nh[i] = nh; a.st.hpos[i] = hpos; a.st.hlen[i] = hlen;
+    if (a.st.counts) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
+        atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
+        if ((i & 31) == 0) atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);
+        atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
+#else
+        a.st.counts[0] += n_pred;
+        a.st.counts[1] += n_corr;
+#endif
+    }
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
+}
+
+// fused multi-tick replay: MR = false single-rate filter, MR = true delayed-measurement fusion
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunArgs<T> a)
 {
     constexpr int N = BIAS ? 15 : 9;
@@ -465,14 +747,26 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
-    run_filter<T, BIAS, DIRECT, SYNTH>(a, i, P, i < a.st.n, vbuf);   // padding lanes still take part in the votes
+    // padding lanes still take part in the votes
+    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
+    else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
 }
 
 // ------------------------------------------------------------------------------------------------
 // single-step kernels (stateless step functions and the tag callback)
 // ------------------------------------------------------------------------------------------------
+// "history <- this single entry" for filter i (cpp:326-339): checkpoint = current state, nothing after it
+template <typename T, class PS>
+QEKF_FN void rebase_history(const DeviceState<T> &st, int64_t i, const Nominal<T> &s, const PS &P)
+{
+    if (!st.xc) return;
+    store_checkpoint<T>(st, i, s, P);
+    st.nh[i] = 0;
+    st.hlen[i] = 1;
+}
+
 // AprilTagSubCallback with one pose shared by all filters (node.cpp:153-176)
-template <typename T, bool BIAS, int BLOCK>
+template <typename T, bool BIAS, bool PF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) deliver_tag_kernel(DeviceState<T> st, Consts<T> c, const double *pose8,
                                                             int force_init, int reinit_bias)
 {
@@ -495,15 +789,17 @@ __global__ void __launch_bounds__(BLOCK) deliver_tag_kernel(DeviceState<T> st, C
         // initialize_state reads the latched apriltag_pos/orien members (cpp:310-313)
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)st.pend[cc * st.ld + i];
-        initialize_state<T, BIAS>(s, P, tag, c, reinit_bias != 0);
+        const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(c, st, i);
+        initialize_state<T, BIAS>(s, P, tag, par, reinit_bias != 0);
         store_filter<T>(st, i, s, P);
+        rebase_history<T>(st, i, s, P);
         flags |= FLAG_INIT;
     }
     st.flags[i] = flags;
 }
 
 // prediction_step applied once to every filter with per-filter inputs u [6][ld] (cpp:346-415)
-template <typename T, bool BIAS, int BLOCK>
+template <typename T, bool BIAS, bool PF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) predict_kernel(DeviceState<T> st, Consts<T> c, const double *u_in)
 {
     constexpr int N = BIAS ? 15 : 9;
@@ -517,14 +813,16 @@ __global__ void __launch_bounds__(BLOCK) predict_kernel(DeviceState<T> st, Const
     T u[6], accel[3];
 #pragma unroll
     for (int cc = 0; cc < 6; ++cc) u[cc] = (T)u_in[cc * st.ld + i];
-    prediction_step<T, BIAS>(s, P, u, c, accel);
+    const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(c, st, i);
+    prediction_step<T, BIAS>(s, P, u, par, accel);
     store_filter<T>(st, i, s, P);
+    rebase_history<T>(st, i, s, P);
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) st.aux[cc * st.ld + i] = accel[cc];
 }
 
 // correction_step applied once to every filter with per-filter tag poses [7][ld] (cpp:417-502)
-template <typename T, bool BIAS, bool DIRECT, int BLOCK>
+template <typename T, bool BIAS, bool DIRECT, bool PF, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) correct_kernel(DeviceState<T> st, Consts<T> c, const double *tag_in)
 {
     constexpr int N = BIAS ? 15 : 9;
@@ -539,8 +837,10 @@ __global__ void __launch_bounds__(BLOCK) correct_kernel(DeviceState<T> st, Const
 #pragma unroll
     for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)tag_in[cc * st.ld + i];
     Observation<T> obs;
-    correction_step<T, BIAS, DIRECT>(s, P, tag, c, obs);
+    const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(c, st, i);
+    correction_step<T, BIAS, DIRECT>(s, P, tag, par, obs);
     store_filter<T>(st, i, s, P);
+    rebase_history<T>(st, i, s, P);
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) st.aux[(3 + cc) * st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll

@@ -76,14 +76,38 @@ template <typename T> Consts<T> make_consts(const qekf_params &p)
         c.tag_py[i] = (T)p.tag_positions[3 * i + 1];
     }
     c.small_ang_tol = (T)p.small_ang_tol;
-    c.meas_delay = (T)p.measurement_delay;
-    c.meas_delay_max = (T)p.measurement_delay_max;
-    c.dyn_offset = (T)p.dyn_measurement_delay_offset;
+    c.meas_delay = p.measurement_delay;
+    c.meas_delay_max = p.measurement_delay_max;
+    c.dyn_offset = p.dyn_measurement_delay_offset;
+    c.dT_nom = 1 / p.update_freq;
     c.limit_measurement_freq = p.limit_measurement_freq;
     c.corner_margin_enbl = p.corner_margin_enbl;
     c.dynamic_meas_delay = p.dynamic_meas_delay;
     return c;
 }
 
+// One filter's column of the per-filter parameter table ([PF_DIM][ld], ekf_core.cuh): the overridable
+// parameters of p plus everything initialize_params derives from them.
+template <typename T> void fill_pf_column(const qekf_params &p, T *col, int64_t ld)
+{
+    const Consts<T> c = make_consts<T>(p);
+    for (int i = 0; i < 12; ++i) col[(PF_Q + i) * ld] = c.Q[i];
+    for (int i = 0; i < 3; ++i) col[(PF_RA + i) * ld] = c.Ra[i];
+    for (int i = 0; i < 6; ++i) { col[(PF_RC + i) * ld] = c.RC[i]; col[(PF_RAS + i) * ld] = c.RA[i]; }
+    for (int i = 0; i < 9; ++i) { col[(PF_D + i) * ld] = c.D[i]; col[(PF_CVC + i) * ld] = c.C_vc[i]; }
+    for (int i = 0; i < 3; ++i) col[(PF_RVCV + i) * ld] = c.r_v_cv[i];
+    for (int i = 0; i < 4; ++i) col[(PF_QVC + i) * ld] = c.q_vc[i];
+}
+
+// largest step delay a correction can use (cpp:199-200) and the ring length that goes with it
+inline int step_of_delay(double delay, double update_freq)
+{
+    const int s = (int)(delay / (1 / update_freq) + 0.5);
+    return s < 1 ? 1 : s;
+}
+inline int ring_length(int dmax, const qekf_params &p)
+{
+    return dmax + 2 * (int)std::ceil(p.update_freq / p.measurement_freq) + 1;
+}
 
 }  // namespace qekf

@@ -3,33 +3,33 @@
 
 namespace qekf {
 
-template <typename T, bool BIAS>
+template <typename T, bool BIAS, bool PF>
 cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
                            int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = deliver_tag_kernel<T, BIAS, BLOCK>;
+    auto kern = deliver_tag_kernel<T, BIAS, PF, BLOCK>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, BLOCK, smem, stream>>>(st, c, pose8, force_init, reinit_bias);
     return cudaGetLastError();
 }
 
-template <typename T, bool BIAS>
+template <typename T, bool BIAS, bool PF>
 cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,
                            cudaStream_t stream)
 {
-    auto kern = predict_kernel<T, BIAS, BLOCK>;
+    auto kern = predict_kernel<T, BIAS, PF, BLOCK>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, BLOCK, smem, stream>>>(st, c, u);
     return cudaGetLastError();
 }
 
-template <typename T, bool BIAS, bool DIRECT>
+template <typename T, bool BIAS, bool DIRECT, bool PF>
 cudaError_t launch_correct(const DeviceState<T> &st, const Consts<T> &c, const double *tag, unsigned grid, size_t smem,
                            cudaStream_t stream)
 {
-    auto kern = correct_kernel<T, BIAS, DIRECT, BLOCK>;
+    auto kern = correct_kernel<T, BIAS, DIRECT, PF, BLOCK>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, BLOCK, smem, stream>>>(st, c, tag);
@@ -55,6 +55,22 @@ cudaError_t launch_reset(const DeviceState<T> &st, const Consts<T> &c, int nstat
 {
     const unsigned g = (unsigned)((st.n + 127) / 128);
     reset_kernel<T><<<g, 128, 0, stream>>>(st, c, nstates, reset_nominal);
+    return cudaGetLastError();
+}
+
+template <typename T> __global__ void rebase_kernel(DeviceState<T> st, int np)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    for (int e = 0; e < 16; ++e) st.xc[e * st.ld + i] = st.x[e * st.ld + i];
+    for (int e = 0; e < np; ++e) st.Pc[e * st.ld + i] = st.P[e * st.ld + i];
+    st.nh[i] = 0;
+    st.hlen[i] = (st.flags[i] & FLAG_INIT) ? 1 : 0;
+}
+
+template <typename T> cudaError_t launch_rebase(const DeviceState<T> &st, int np, cudaStream_t stream)
+{
+    rebase_kernel<T><<<(unsigned)((st.n + 127) / 128), 128, 0, stream>>>(st, np);
     return cudaGetLastError();
 }
 
@@ -107,20 +123,25 @@ template <typename T> cudaError_t launch_fma_peak(T *sink, int iters, unsigned g
 template cudaError_t launch_fma_peak<double>(double *, int, unsigned, unsigned, cudaStream_t);
 template cudaError_t launch_fma_peak<float>(float *, int, unsigned, unsigned, cudaStream_t);
 
-#define INST_TB(T, B)                                                                                                   \
-    template cudaError_t launch_deliver<T, B>(const DeviceState<T> &, const Consts<T> &, const double *, int, int,      \
-                                              unsigned, size_t, cudaStream_t);                                         \
-    template cudaError_t launch_predict<T, B>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned,      \
-                                              size_t, cudaStream_t);                                                   \
-    template cudaError_t launch_correct<T, B, true>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned, \
-                                                    size_t, cudaStream_t);                                             \
-    template cudaError_t launch_correct<T, B, false>(const DeviceState<T> &, const Consts<T> &, const double *,         \
-                                                     unsigned, size_t, cudaStream_t);
-INST_TB(double, true)
-INST_TB(double, false)
-INST_TB(float, true)
-INST_TB(float, false)
+#define INST_TB(T, B, F)                                                                                                \
+    template cudaError_t launch_deliver<T, B, F>(const DeviceState<T> &, const Consts<T> &, const double *, int, int,   \
+                                                 unsigned, size_t, cudaStream_t);                                      \
+    template cudaError_t launch_predict<T, B, F>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned,   \
+                                                 size_t, cudaStream_t);                                                \
+    template cudaError_t launch_correct<T, B, true, F>(const DeviceState<T> &, const Consts<T> &, const double *,       \
+                                                       unsigned, size_t, cudaStream_t);                                \
+    template cudaError_t launch_correct<T, B, false, F>(const DeviceState<T> &, const Consts<T> &, const double *,      \
+                                                        unsigned, size_t, cudaStream_t);
+INST_TB(double, true, false)
+INST_TB(double, false, false)
+INST_TB(float, true, false)
+INST_TB(float, false, false)
+INST_TB(double, true, true)
+INST_TB(double, false, true)
+INST_TB(float, true, true)
+INST_TB(float, false, true)
 #define INST_T(T)                                                                                                       \
+    template cudaError_t launch_rebase<T>(const DeviceState<T> &, int, cudaStream_t);                                   \
     template cudaError_t launch_reset<T>(const DeviceState<T> &, const Consts<T> &, int, int, cudaStream_t);            \
     template cudaError_t launch_dump<T>(const RunArgs<T> &, int64_t, int64_t, int64_t, double *, double *, uint8_t *,   \
                                         double *, cudaStream_t);

@@ -10,23 +10,26 @@ namespace qekf {
 
 constexpr int BLOCK = 224;  // 7 warps: 7 x 30 KB of FP64 covariance fill one SM's shared memory (1 CTA / SM)
 
-template <typename T, bool BIAS, bool DIRECT, bool SYNTH>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);
 
-template <typename T, bool BIAS>
+template <typename T, bool BIAS, bool PF>
 cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
                            int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream);
 
-template <typename T, bool BIAS>
+template <typename T, bool BIAS, bool PF>
 cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,
                            cudaStream_t stream);
 
-template <typename T, bool BIAS, bool DIRECT>
+template <typename T, bool BIAS, bool DIRECT, bool PF>
 cudaError_t launch_correct(const DeviceState<T> &st, const Consts<T> &c, const double *tag, unsigned grid, size_t smem,
                            cudaStream_t stream);
 
 template <typename T>
 cudaError_t launch_reset(const DeviceState<T> &st, const Consts<T> &c, int nstates, int reset_nominal, cudaStream_t stream);
+
+// history <- current head for every filter (checkpoint = x / P, no entries after it)
+template <typename T> cudaError_t launch_rebase(const DeviceState<T> &st, int np, cudaStream_t stream);
 
 template <typename T>
 cudaError_t launch_dump(const RunArgs<T> &a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,

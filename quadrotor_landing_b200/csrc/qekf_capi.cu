@@ -53,6 +53,15 @@ struct qekf_handle {
     double *pend = nullptr;
     int32_t *flags = nullptr, *upds = nullptr;
     unsigned long long *counts = nullptr;
+    // delayed-measurement fusion (multirate_ekf): lagged checkpoint + IMU ring, see ekf_kernels.cuh
+    void *xc = nullptr, *Pc = nullptr, *ring = nullptr;
+    int32_t *nh = nullptr, *hpos = nullptr, *hlen = nullptr;
+    int ring_len = 0, dmax = 1;
+    // per-filter parameter overrides: host copies [dim][N] per field, derived device tables
+    std::vector<double> pf_host[5];
+    bool pf_on = false;
+    void *pf = nullptr;
+    double *pf_delay = nullptr;
     // per-tick interface staging
     double *d_tick = nullptr;        // [6 imu][8 tag]
     double *h_tick = nullptr;        // pinned mirror
@@ -78,6 +87,11 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     DeviceState<T> s;
     s.x = (T *)h->x; s.P = (T *)h->P; s.aux = (T *)h->aux; s.pend = h->pend;
     s.flags = h->flags; s.upds = h->upds; s.counts = h->counts; s.ld = h->ld; s.n = h->n;
+    s.xc = (T *)h->xc; s.Pc = (T *)h->Pc; s.ring = (T *)h->ring;
+    s.nh = h->nh; s.hpos = h->hpos; s.hlen = h->hlen;
+    s.ring_len = h->ring_len; s.dmax_m1 = h->dmax - 1;
+    s.pf = h->pf_on ? (const T *)h->pf : nullptr;
+    s.pf_delay = h->pf_on ? h->pf_delay : nullptr;
     return s;
 }
 
@@ -106,11 +120,69 @@ int free_state(qekf_handle *h)
     cudaFree(h->x); cudaFree(h->P); cudaFree(h->aux); cudaFree(h->pend);
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
     cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared); cudaFree(h->counts);
+    cudaFree(h->xc); cudaFree(h->Pc); cudaFree(h->ring); cudaFree(h->nh); cudaFree(h->hpos); cudaFree(h->hlen);
+    cudaFree(h->pf); cudaFree(h->pf_delay);
+    h->xc = h->Pc = h->ring = nullptr; h->nh = h->hpos = h->hlen = nullptr; h->ring_len = 0;
+    h->pf = nullptr; h->pf_delay = nullptr; h->pf_on = false;
+    for (auto &v : h->pf_host) v.clear();
     h->counts = nullptr;
     h->stats_acc = h->stats_red = nullptr; h->stats_bins = 0; h->d_shared = nullptr; h->d_shared_bytes = 0;
     if (h->h_tick) cudaFreeHost(h->h_tick);
     h->x = h->P = h->aux = nullptr; h->pend = nullptr; h->flags = h->upds = nullptr;
     h->d_tick = nullptr; h->h_tick = nullptr; h->d_in = nullptr; h->d_in_bytes = 0;
+    return QEKF_OK;
+}
+
+// largest step delay a correction of this handle can use (cpp:199-200)
+int max_step_delay(const qekf_handle *h)
+{
+    if (h->p.dynamic_meas_delay) return step_of_delay(h->p.measurement_delay_max, h->p.update_freq);
+    int d = step_of_delay(h->p.measurement_delay, h->p.update_freq);
+    const std::vector<double> &v = h->pf_host[QEKF_PF_DELAY];
+    for (int64_t i = 0; i < (int64_t)v.size() / 2; ++i) {
+        const int di = step_of_delay(v[(size_t)i], h->p.update_freq);
+        if (di > d) d = di;
+    }
+    return d;
+}
+
+// (re)allocate the delayed-fusion storage for the current parameters; histories restart from the heads
+int alloc_history(qekf_handle *h)
+{
+    if (!h->p.multirate_ekf) return QEKF_OK;
+    const size_t ld = (size_t)h->ld;
+    const int dmax = max_step_delay(h);
+    const int L = ring_length(dmax, h->p);
+    if (!h->xc) {
+        CUDA_TRY(cudaMalloc(&h->xc, 16 * ld * h->tsize));
+        CUDA_TRY(cudaMalloc(&h->Pc, (size_t)h->np * ld * h->tsize));
+        CUDA_TRY(cudaMalloc(&h->nh, ld * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->hpos, ld * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->hlen, ld * sizeof(int32_t)));
+        CUDA_TRY(cudaMemsetAsync(h->xc, 0, 16 * ld * h->tsize, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->Pc, 0, (size_t)h->np * ld * h->tsize, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->nh, 0, ld * sizeof(int32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->hpos, 0, ld * sizeof(int32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->hlen, 0, ld * sizeof(int32_t), h->stream));
+    }
+    if (L != h->ring_len) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->ring);
+        h->ring = nullptr; h->ring_len = 0;
+        CUDA_TRY(cudaMalloc(&h->ring, (size_t)L * 6 * ld * h->tsize));
+        CUDA_TRY(cudaMemsetAsync(h->ring, 0, (size_t)L * 6 * ld * h->tsize, h->stream));
+        h->ring_len = L;
+    }
+    h->dmax = dmax;
+    return QEKF_OK;
+}
+
+// history <- the current head, for every filter (a ring that changed size, or parameters that changed)
+int rebase_all(qekf_handle *h)
+{
+    if (!h->p.multirate_ekf || !h->xc) return QEKF_OK;
+    if (h->precision == QEKF_FP64) CUDA_TRY(launch_rebase<double>(dstate<double>(h), h->np, h->stream));
+    else CUDA_TRY(launch_rebase<float>(dstate<float>(h), h->np, h->stream));
     return QEKF_OK;
 }
 
@@ -136,7 +208,7 @@ int alloc_state(qekf_handle *h)
     CUDA_TRY(cudaMemsetAsync(h->pend, 0, PEND_DIM * ld * sizeof(double), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->flags, 0, ld * sizeof(int32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->upds, 0, ld * sizeof(int32_t), h->stream));
-    return QEKF_OK;
+    return alloc_history(h);
 }
 
 int reset_cov(qekf_handle *h, bool reset_nominal)
@@ -153,7 +225,12 @@ int check_params(const qekf_params *p)
     if (!p) return fail(QEKF_ERR_BAD_ARG, "params is NULL");
     if (!(p->update_freq > 0) || !(p->measurement_freq > 0)) return fail(QEKF_ERR_BAD_ARG, "rates must be positive");
     if (p->n_tags < 0 || p->n_tags > QEKF_MAX_TAGS) return fail(QEKF_ERR_BAD_ARG, "n_tags out of range");
-    if (p->multirate_ekf) return fail(QEKF_ERR_UNSUPPORTED, "multirate_ekf is not built yet");
+    if (p->multirate_ekf) {
+        if (!(p->measurement_delay_max >= 0) || !(p->measurement_delay >= 0))
+            return fail(QEKF_ERR_BAD_ARG, "measurement delays must be non-negative");
+        if (step_of_delay(p->dynamic_meas_delay ? p->measurement_delay_max : p->measurement_delay, p->update_freq) > 4096)
+            return fail(QEKF_ERR_BAD_ARG, "measurement delay spans more than 4096 ticks");
+    }
     return QEKF_OK;
 }
 
@@ -176,10 +253,20 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
             a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
             a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
         }
-        CUDA_TRY((launch_run<T, BIAS, DIRECT, true>(a, grid_of(h), smem_bytes(h), h->stream)));
-    } else {
-        CUDA_TRY((launch_run<T, BIAS, DIRECT, false>(a, grid_of(h), smem_bytes(h), h->stream)));
     }
+    const bool mr = h->p.multirate_ekf != 0, pf = h->pf_on;
+#define LAUNCH_(S, MR_, PF_) CUDA_TRY((launch_run<T, BIAS, DIRECT, S, MR_, PF_>(a, grid_of(h), smem_bytes(h), h->stream)))
+#define LAUNCH_S(S)                                                       \
+    do {                                                                  \
+        if (mr && pf) LAUNCH_(S, true, true);                             \
+        else if (mr) LAUNCH_(S, true, false);                             \
+        else if (pf) LAUNCH_(S, false, true);                             \
+        else LAUNCH_(S, false, false);                                    \
+    } while (0)
+    if (ns) LAUNCH_S(true);
+    else LAUNCH_S(false);
+#undef LAUNCH_S
+#undef LAUNCH_
     h->launches++;
     return QEKF_OK;
 }
@@ -241,6 +328,35 @@ int ensure_in(qekf_handle *h, size_t bytes)
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// derive the device tables of the per-filter overrides: initialize_params (cpp:87-125) once per filter
+template <typename T> int rebuild_pf_t(qekf_handle *h)
+{
+    const size_t N = (size_t)h->n, ld = (size_t)h->ld;
+    std::vector<T> tab((size_t)PF_DIM * ld, T(0));
+    std::vector<double> dl(2 * ld, 0.0);
+    qekf_params p = h->p;
+    for (size_t i = 0; i < N; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            p.Q_a[k] = h->pf_host[QEKF_PF_Q][(0 + k) * N + i]; p.Q_w[k] = h->pf_host[QEKF_PF_Q][(3 + k) * N + i];
+            p.Q_ab[k] = h->pf_host[QEKF_PF_Q][(6 + k) * N + i]; p.Q_wb[k] = h->pf_host[QEKF_PF_Q][(9 + k) * N + i];
+            p.R_r[k] = h->pf_host[QEKF_PF_R][(0 + k) * N + i]; p.R_ang[k] = h->pf_host[QEKF_PF_R][(3 + k) * N + i];
+            p.r_v_cv[k] = h->pf_host[QEKF_PF_R_V_CV][k * N + i];
+        }
+        for (int k = 0; k < 4; ++k) p.q_vc[k] = h->pf_host[QEKF_PF_Q_VC][k * N + i];
+        fill_pf_column<T>(p, tab.data() + i, (int64_t)ld);
+        dl[i] = h->pf_host[QEKF_PF_DELAY][0 * N + i];
+        dl[ld + i] = h->pf_host[QEKF_PF_DELAY][1 * N + i];
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->pf, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->pf_delay, dl.data(), dl.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return QEKF_OK;
+}
+int rebuild_pf(qekf_handle *h)
+{
+    return h->precision == QEKF_FP64 ? rebuild_pf_t<double>(h) : rebuild_pf_t<float>(h);
+}
 
 }  // namespace
 
@@ -340,7 +456,15 @@ int qekf_set_params(qekf_handle *h, const qekf_params *p)
         if (rc) return rc;
         return reset_cov(h, true);
     }
-    return reset_cov(h, false);   // initialize_params: cov_pert = cov_init (cpp:114)
+    rc = reset_cov(h, false);     // initialize_params: cov_pert = cov_init (cpp:114)
+    if (rc) return rc;
+    if (h->pf_on) { rc = rebuild_pf(h); if (rc) return rc; }
+    if (!h->p.multirate_ekf) return QEKF_OK;
+    // Delayed fusion: the history restarts from the current head.  (The reference keeps its old history
+    // vectors here, so its next delayed correction would silently discard the covariance reset.)
+    rc = alloc_history(h);
+    if (rc) return rc;
+    return rebase_all(h);
 }
 
 int qekf_get_params(const qekf_handle *h, qekf_params *p)
@@ -352,9 +476,44 @@ int qekf_get_params(const qekf_handle *h, qekf_params *p)
 
 int qekf_set_filter_params(qekf_handle *h, int field, const double *values)
 {
-    (void)field; (void)values;
-    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
-    return fail(QEKF_ERR_UNSUPPORTED, "per-filter parameter overrides are not built yet");
+    static const int dims[5] = { 12, 6, 3, 4, 2 };
+    if (!h || !values) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (field < 0 || field > QEKF_PF_DELAY) return fail(QEKF_ERR_BAD_ARG, "unknown per-filter field");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t N = (size_t)h->n;
+    if (!h->pf_on) {
+        // first override: every field starts from the handle-wide parameters
+        const qekf_params &p = h->p;
+        for (int f = 0; f < 5; ++f) h->pf_host[f].assign((size_t)dims[f] * N, 0.0);
+        for (size_t i = 0; i < N; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                h->pf_host[QEKF_PF_Q][(0 + k) * N + i] = p.Q_a[k]; h->pf_host[QEKF_PF_Q][(3 + k) * N + i] = p.Q_w[k];
+                h->pf_host[QEKF_PF_Q][(6 + k) * N + i] = p.Q_ab[k]; h->pf_host[QEKF_PF_Q][(9 + k) * N + i] = p.Q_wb[k];
+                h->pf_host[QEKF_PF_R][(0 + k) * N + i] = p.R_r[k]; h->pf_host[QEKF_PF_R][(3 + k) * N + i] = p.R_ang[k];
+                h->pf_host[QEKF_PF_R_V_CV][k * N + i] = p.r_v_cv[k];
+            }
+            for (int k = 0; k < 4; ++k) h->pf_host[QEKF_PF_Q_VC][k * N + i] = p.q_vc[k];
+            h->pf_host[QEKF_PF_DELAY][0 * N + i] = p.measurement_delay;
+            h->pf_host[QEKF_PF_DELAY][1 * N + i] = p.dyn_measurement_delay_offset;
+        }
+        CUDA_TRY(cudaMalloc(&h->pf, (size_t)PF_DIM * (size_t)h->ld * h->tsize));
+        CUDA_TRY(cudaMalloc(&h->pf_delay, 2 * (size_t)h->ld * sizeof(double)));
+        h->pf_on = true;
+    }
+    if (field == QEKF_PF_DELAY)
+        for (size_t i = 0; i < N; ++i)
+            if (!(values[i] >= 0) || step_of_delay(values[i], h->p.update_freq) > 4096)
+                return fail(QEKF_ERR_BAD_ARG, "per-filter measurement_delay out of range");
+    std::memcpy(h->pf_host[field].data(), values, (size_t)dims[field] * N * sizeof(double));
+    int rc = rebuild_pf(h);
+    if (rc) return rc;
+    if (field == QEKF_PF_DELAY && h->p.multirate_ekf) {
+        const int old_len = h->ring_len;
+        rc = alloc_history(h);
+        if (rc) return rc;
+        if (h->ring_len != old_len) return rebase_all(h);
+    }
+    return QEKF_OK;
 }
 
 int qekf_num_states(const qekf_handle *h) { return h ? h->nstates : 0; }
@@ -390,9 +549,15 @@ int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3])
 
 static int deliver(qekf_handle *h, int force_init, int reinit_bias)
 {
-#define CALL_DELIVER(T, B, D)                                                                                    \
-    CUDA_TRY((launch_deliver<T, B>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init, reinit_bias,   \
-                                   grid_of(h), smem_bytes(h), h->stream)))
+#define CALL_DELIVER(T, B, D)                                                                                          \
+    do {                                                                                                               \
+        if (h->pf_on)                                                                                                  \
+            CUDA_TRY((launch_deliver<T, B, true>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init,        \
+                                                 reinit_bias, grid_of(h), smem_bytes(h), h->stream)));                 \
+        else                                                                                                           \
+            CUDA_TRY((launch_deliver<T, B, false>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init,       \
+                                                  reinit_bias, grid_of(h), smem_bytes(h), h->stream)));                \
+    } while (0)
     QEKF_DISPATCH(h, CALL_DELIVER);
 #undef CALL_DELIVER
     h->launches++;
@@ -536,9 +701,13 @@ int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6
     if (!range_ok(h, first, count) || !flags6) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL output");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    std::vector<int32_t> fl((size_t)count), up((size_t)count);
+    std::vector<int32_t> fl((size_t)count), up((size_t)count), hl;
     CUDA_TRY(cudaMemcpy(fl.data(), h->flags + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(up.data(), h->upds + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    if (h->hlen) {
+        hl.resize((size_t)count);
+        CUDA_TRY(cudaMemcpy(hl.data(), h->hlen + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    }
     for (int64_t i = 0; i < count; ++i) {
         const int32_t f = fl[(size_t)i];
         flags6[0 * count + i] = (f & FLAG_INIT) ? 1 : 0;
@@ -546,7 +715,8 @@ int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6
         flags6[2 * count + i] = (f & FLAG_CORRECTED) ? 1 : 0;
         flags6[3 * count + i] = (f & FLAG_ACTIVE) ? 1 : 0;
         flags6[4 * count + i] = up[(size_t)i];
-        flags6[5 * count + i] = (f & FLAG_INIT) ? 1 : 0;   // single-rate: history holds one entry
+        // x_hist.size(): single-rate filters keep the one entry initialize_state wrote (cpp:326-339)
+        flags6[5 * count + i] = (f & FLAG_INIT) ? (hl.empty() ? 1 : hl[(size_t)i]) : 0;
     }
     return QEKF_OK;
 }
@@ -569,6 +739,14 @@ int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x
     CUDA_TRY(cudaMemcpy(fl.data(), h->flags + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
     for (auto &f : fl) f |= FLAG_INIT;
     CUDA_TRY(cudaMemcpy(h->flags + first, fl.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+    if (h->xc) {   // history <- this entry
+        rc = store_rows(h, h->xc, 16, first, count, x16);
+        if (!rc) rc = store_rows(h, h->Pc, h->np, first, count, packed.data());
+        if (rc) return rc;
+        std::vector<int32_t> ones((size_t)count, 1);
+        CUDA_TRY(cudaMemset(h->nh + first, 0, (size_t)count * 4));
+        CUDA_TRY(cudaMemcpy(h->hlen + first, ones.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+    }
     return QEKF_OK;
 }
 
@@ -590,9 +768,15 @@ int qekf_prediction_step(qekf_handle *h, const double *u)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, u, 6);
     if (rc) return rc;
-#define CALL_PRED(T, B, D)                                                                                   \
-    CUDA_TRY((launch_predict<T, B>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in, grid_of(h),  \
-                                   smem_bytes(h), h->stream)))
+#define CALL_PRED(T, B, D)                                                                                         \
+    do {                                                                                                           \
+        if (h->pf_on)                                                                                              \
+            CUDA_TRY((launch_predict<T, B, true>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in,      \
+                                                 grid_of(h), smem_bytes(h), h->stream)));                          \
+        else                                                                                                       \
+            CUDA_TRY((launch_predict<T, B, false>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in,     \
+                                                  grid_of(h), smem_bytes(h), h->stream)));                         \
+    } while (0)
     QEKF_DISPATCH(h, CALL_PRED);
 #undef CALL_PRED
     h->launches++;
@@ -605,9 +789,15 @@ int qekf_correction_step(qekf_handle *h, const double *tag_pose)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, tag_pose, 7);
     if (rc) return rc;
-#define CALL_CORR(T, B, D)                                                                                      \
-    CUDA_TRY((launch_correct<T, B, D>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in, grid_of(h),  \
-                                      smem_bytes(h), h->stream)))
+#define CALL_CORR(T, B, D)                                                                                         \
+    do {                                                                                                           \
+        if (h->pf_on)                                                                                              \
+            CUDA_TRY((launch_correct<T, B, D, true>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in,   \
+                                                    grid_of(h), smem_bytes(h), h->stream)));                       \
+        else                                                                                                       \
+            CUDA_TRY((launch_correct<T, B, D, false>(dstate<T>(h), make_consts<T>(h->p), (const double *)h->d_in,  \
+                                                     grid_of(h), smem_bytes(h), h->stream)));                      \
+    } while (0)
     QEKF_DISPATCH(h, CALL_CORR);
 #undef CALL_CORR
     CUDA_TRY(cudaGetLastError());
@@ -803,6 +993,12 @@ int qekf_reset_filters(qekf_handle *h)
     CUDA_TRY(cudaMemsetAsync(h->pend, 0, PEND_DIM * ld * sizeof(double), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->flags, 0, ld * sizeof(int32_t), h->stream));
     CUDA_TRY(cudaMemsetAsync(h->upds, 0, ld * sizeof(int32_t), h->stream));
+    if (h->xc) {
+        CUDA_TRY(cudaMemsetAsync(h->xc, 0, 16 * ld * h->tsize, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->nh, 0, ld * sizeof(int32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->hpos, 0, ld * sizeof(int32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->hlen, 0, ld * sizeof(int32_t), h->stream));
+    }
     return reset_cov(h, true);
 }
 

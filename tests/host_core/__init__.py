@@ -69,12 +69,51 @@ class HostBatch:
         self.np_ = self.n * (self.n + 1) // 2
         self.x = np.zeros((16, self.N)); self.x[9] = 1.0
         self.Ppk = np.zeros((self.np_, self.N))
+        ci = [params.r_cov_init, params.v_cov_init, params.ang_cov_init, params.ab_cov_init, params.wb_cov_init]
+        e = 0
+        for a in range(self.n):          # cov_pert = cov_init (cpp:114), as the product's reset kernel does
+            for b in range(a, self.n):
+                if a == b:
+                    self.Ppk[e] = ci[a // 3]
+                e += 1
         self.aux = np.zeros((11, self.N)); self.aux[9] = 1.0
         self.pend = np.zeros((8, self.N))
         self.flags = np.zeros(self.N, dtype=np.int32)
         self.upds = np.zeros(self.N, dtype=np.int32)
+        self.pf = None          # per-filter overrides: list of 5 arrays [dim][N] (QEKF_PF_* order)
+        self._hist = None
+
+    PF_DIMS = (12, 6, 3, 4, 2)
+
+    def set_filter_params(self, field, values):
+        p = self.p
+        if self.pf is None:
+            N = self.N
+            one = lambda v: np.repeat(np.asarray(v, dtype=np.float64)[:, None], N, axis=1)
+            self.pf = [one(list(p.Q_a) + list(p.Q_w) + list(p.Q_ab) + list(p.Q_wb)), one(list(p.R_r) + list(p.R_ang)),
+                       one(list(p.r_v_cv)), one(list(p.q_vc)), one([p.measurement_delay, p.dyn_measurement_delay_offset])]
+        v = _f64(values)
+        assert v.shape == (self.PF_DIMS[field], self.N)
+        self.pf[field] = v.copy()
+        self._hist = None
+
+    def _history(self):
+        if self._hist is None:
+            geo = np.zeros(2, dtype=np.int32)
+            d = _dp(np.ascontiguousarray(self.pf[4][0])) if self.pf is not None else None
+            L = lib()
+            L.hc_ring_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int32)]
+            L.hc_ring_geometry(C.byref(self.p), d, self.N, geo.ctypes.data_as(C.POINTER(C.c_int32)))
+            dmax, ring_len = int(geo[0]), int(geo[1])
+            self._hist = dict(xc=np.zeros((16, self.N)), Pc=np.zeros((self.np_, self.N)),
+                              ring=np.zeros((ring_len, 6, self.N)), nh=np.zeros(self.N, dtype=np.int32),
+                              hpos=np.zeros(self.N, dtype=np.int32), hlen=np.zeros(self.N, dtype=np.int32),
+                              ring_len=ring_len, dmax=dmax)
+        return self._hist
 
     def run(self, k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid=None, t_start=0.0):
+        if self.p.multirate_ekf or self.pf is not None:
+            return self._run_ext(k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid, t_start)
         imu = _f64(imu); tag_pose = _f64(tag_pose); tag_stamp = _f64(tag_stamp)
         tag_step = np.ascontiguousarray(tag_step, dtype=np.int32)
         M = tag_step.shape[0]
@@ -90,6 +129,34 @@ class HostBatch:
                  tag_step.ctypes.data_as(C.POINTER(C.c_int32)), _dp(tag_pose), _dp(tag_stamp), vptr, float(t_start),
                  _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
                  self.flags.ctypes.data_as(C.POINTER(C.c_int32)), self.upds.ctypes.data_as(C.POINTER(C.c_int32)))
+
+    def _run_ext(self, k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid, t_start):
+        imu = _f64(imu); tag_pose = _f64(tag_pose); tag_stamp = _f64(tag_stamp)
+        tag_step = np.ascontiguousarray(tag_step, dtype=np.int32)
+        M = tag_step.shape[0]
+        vptr = None
+        if tag_valid is not None:
+            tag_valid = np.ascontiguousarray(tag_valid, dtype=np.uint8)
+            vptr = tag_valid.ctypes.data_as(C.POINTER(C.c_uint8))
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        i32 = lambda a: a.ctypes.data_as(ip)
+        L = lib()
+        L.hc_run_ext.argtypes = ([C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp,
+                                  C.POINTER(C.c_uint8), C.c_double] + [dp] * 4 + [ip] * 2 + [dp] * 3 + [ip] * 3 +
+                                 [C.c_int32, C.c_int32] + [dp] * 5)
+        if self.p.multirate_ekf:
+            h = self._history()
+            hist = [_dp(h["xc"]), _dp(h["Pc"]), _dp(h["ring"]), i32(h["nh"]), i32(h["hpos"]), i32(h["hlen"]),
+                    h["ring_len"], h["dmax"]]
+        else:
+            hist = [None, None, None, None, None, None, 0, 1]
+        pf = [_dp(a) for a in self.pf] if self.pf is not None else [None] * 5
+        L.hc_run_ext(C.byref(self.p), int(self.prec), self.N, int(k0), int(n_steps), _dp(imu), M, i32(tag_step),
+                     _dp(tag_pose), _dp(tag_stamp), vptr, float(t_start), _dp(self.x), _dp(self.Ppk), _dp(self.aux),
+                     _dp(self.pend), i32(self.flags), i32(self.upds), *hist, *pf)
+
+    def history_length(self):
+        return self._history()["hlen"].copy() if self.p.multirate_ekf else (self.flags & 1)
 
     def run_mc(self, scn, noise, k0=0, n_steps=None, stats=None, stride=0):
         """Monte-Carlo replay (shared clean scenario + per-filter noise).  stats: array [32][n_bins][20] or None."""

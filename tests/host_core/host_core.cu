@@ -78,7 +78,7 @@ template <typename T, bool BIAS> void predict_t(const qekf_params *p, const doub
     unpack<T, BIAS>(x, Pin, s, P);
     T uu[6], a[3];
     for (int k = 0; k < 6; ++k) uu[k] = (T)u[k];
-    prediction_step<T, BIAS>(s, P, uu, c, a);
+    prediction_step<T, BIAS>(s, P, uu, ParU<T>{ c }, a);
     pack<T, BIAS>(s, P, xo, Po);
     for (int k = 0; k < 3; ++k) acc[k] = a[k];
 }
@@ -93,7 +93,7 @@ template <typename T, bool BIAS, bool DIRECT> void correct_t(const qekf_params *
     T tg[7];
     for (int k = 0; k < 7; ++k) tg[k] = (T)tag[k];
     Observation<T> obs;
-    correction_step<T, BIAS, DIRECT>(s, P, tg, c, obs);
+    correction_step<T, BIAS, DIRECT>(s, P, tg, ParU<T>{ c }, obs);
     pack<T, BIAS>(s, P, xo, Po);
     for (int k = 0; k < 3; ++k) obs7[k] = obs.r_t_vt_obs[k];
     for (int k = 0; k < 4; ++k) obs7[3 + k] = obs.q_tv_obs[k];
@@ -106,11 +106,19 @@ struct McArgs {           // Monte-Carlo (synthetic-noise) extras; ns == nullptr
     int32_t n_bins, stride;
 };
 
+// delayed-fusion state and per-filter overrides of a host batch (all optional)
+struct ExtArgs {
+    double *xc, *Pc, *ring;          // [16][N], [NP][N], [L][6][N]
+    int32_t *nh, *hpos, *hlen;       // [N]
+    int32_t ring_len, dmax;
+    const double *pf[5];             // per-filter overrides [dim][N] per QEKF_PF_* field, or all NULL
+};
+
 template <typename T, bool BIAS, bool DIRECT>
 void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
            const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
            double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
-           const McArgs *mc = nullptr)
+           const McArgs *mc = nullptr, const ExtArgs *ext = nullptr)
 {
     constexpr int NS = BIAS ? 15 : 9;
     constexpr int NP = NS * (NS + 1) / 2;
@@ -140,14 +148,58 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
             a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
         }
     }
+    const bool mr = p->multirate_ekf != 0;
+    const bool pf = ext && ext->pf[0];
+    std::vector<T> xcs, Pcs, rings, pft;
+    std::vector<double> pfd;
+    if (mr) {
+        xcs.resize(16 * N); Pcs.resize((size_t)NP * N); rings.resize((size_t)ext->ring_len * 6 * N);
+        for (size_t k = 0; k < xcs.size(); ++k) xcs[k] = (T)ext->xc[k];
+        for (size_t k = 0; k < Pcs.size(); ++k) Pcs[k] = (T)ext->Pc[k];
+        for (size_t k = 0; k < rings.size(); ++k) rings[k] = (T)ext->ring[k];
+        a.st.xc = xcs.data(); a.st.Pc = Pcs.data(); a.st.ring = rings.data();
+        a.st.nh = ext->nh; a.st.hpos = ext->hpos; a.st.hlen = ext->hlen;
+        a.st.ring_len = ext->ring_len; a.st.dmax_m1 = ext->dmax - 1;
+    }
+    if (pf) {
+        pft.assign((size_t)PF_DIM * N, T(0));
+        pfd.assign(2 * (size_t)N, 0.0);
+        qekf_params q = *p;
+        for (int64_t i = 0; i < N; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                q.Q_a[k] = ext->pf[0][(0 + k) * N + i]; q.Q_w[k] = ext->pf[0][(3 + k) * N + i];
+                q.Q_ab[k] = ext->pf[0][(6 + k) * N + i]; q.Q_wb[k] = ext->pf[0][(9 + k) * N + i];
+                q.R_r[k] = ext->pf[1][(0 + k) * N + i]; q.R_ang[k] = ext->pf[1][(3 + k) * N + i];
+                q.r_v_cv[k] = ext->pf[2][k * N + i];
+            }
+            for (int k = 0; k < 4; ++k) q.q_vc[k] = ext->pf[3][k * N + i];
+            fill_pf_column<T>(q, pft.data() + i, N);
+            pfd[i] = ext->pf[4][i]; pfd[N + i] = ext->pf[4][N + i];
+        }
+        a.st.pf = pft.data(); a.st.pf_delay = pfd.data();
+    }
+    const bool synth = mc && mc->ns;
     for (int64_t i = 0; i < N; ++i) {
         PLocal<T, NS> P;
-        if (mc && mc->ns) run_filter<T, BIAS, DIRECT, true>(a, i, P);
-        else run_filter<T, BIAS, DIRECT, false>(a, i, P);
+#define RUN_(S, F)                                                         \
+        do {                                                               \
+            if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P);         \
+            else run_filter<T, BIAS, DIRECT, S, F>(a, i, P);               \
+        } while (0)
+        if (synth && pf) RUN_(true, true);
+        else if (synth) RUN_(true, false);
+        else if (pf) RUN_(false, true);
+        else RUN_(false, false);
+#undef RUN_
     }
     for (size_t k = 0; k < xs.size(); ++k) x[k] = xs[k];
     for (size_t k = 0; k < Ps.size(); ++k) Ppk[k] = Ps[k];
     for (size_t k = 0; k < as.size(); ++k) aux[k] = as[k];
+    if (mr) {
+        for (size_t k = 0; k < xcs.size(); ++k) ext->xc[k] = xcs[k];
+        for (size_t k = 0; k < Pcs.size(); ++k) ext->Pc[k] = Pcs[k];
+        for (size_t k = 0; k < rings.size(); ++k) ext->ring[k] = rings[k];
+    }
 }
 
 }  // namespace
@@ -176,13 +228,13 @@ template <bool BIAS, bool DIRECT> static void count_t(const qekf_params *p, doub
         for (int j = i; j < N; ++j) P.st(i, j, Cnt(i == j ? 0.1 : 0.001 * (i + j)));
     Cnt u[6] = { Cnt(0.1), Cnt(-0.2), Cnt(9.7), Cnt(0.01), Cnt(-0.02), Cnt(0.05) }, acc[3];
     Cnt::flops = 0;
-    prediction_step<Cnt, BIAS>(s, P, u, c, acc);
+    prediction_step<Cnt, BIAS>(s, P, u, ParU<Cnt>{ c }, acc);
     out[0] = (double)Cnt::flops;
     // a tag pose close to the prediction
     Cnt tag[7] = { Cnt(0.05), Cnt(-0.1), Cnt(2.4), Cnt(0.70), Cnt(-0.71), Cnt(0.03), Cnt(0.02) };
     Observation<Cnt> obs;
     Cnt::flops = 0;
-    correction_step<Cnt, BIAS, DIRECT>(s, P, tag, c, obs);
+    correction_step<Cnt, BIAS, DIRECT>(s, P, tag, ParU<Cnt>{ c }, obs);
     out[1] = (double)Cnt::flops;
 }
 
@@ -224,6 +276,33 @@ void hc_run(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_ste
 #define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds)
     HC_DISPATCH(prec, p, C_);
 #undef C_
+}
+
+// hc_run with delayed-fusion state and/or per-filter overrides
+void hc_run_ext(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
+                const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
+                double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+                double *xc, double *Pc, double *ring, int32_t *nh, int32_t *hpos, int32_t *hlen, int32_t ring_len,
+                int32_t dmax, const double *pf_q, const double *pf_r, const double *pf_rvcv, const double *pf_qvc,
+                const double *pf_delay)
+{
+    ExtArgs e = { xc, Pc, ring, nh, hpos, hlen, ring_len, dmax, { pf_q, pf_r, pf_rvcv, pf_qvc, pf_delay } };
+#define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds, nullptr, &e)
+    HC_DISPATCH(prec, p, C_);
+#undef C_
+}
+
+// ring geometry the product derives for (params, per-filter delays): out[0] = dmax, out[1] = ring length
+void hc_ring_geometry(const qekf_params *p, const double *pf_delay, int64_t N, int32_t *out)
+{
+    int d = step_of_delay(p->dynamic_meas_delay ? p->measurement_delay_max : p->measurement_delay, p->update_freq);
+    if (!p->dynamic_meas_delay && pf_delay)
+        for (int64_t i = 0; i < N; ++i) {
+            const int di = step_of_delay(pf_delay[i], p->update_freq);
+            if (di > d) d = di;
+        }
+    out[0] = d;
+    out[1] = ring_length(d, *p);
 }
 
 void hc_count_flops(const qekf_params *p, double *out)
