@@ -182,7 +182,10 @@ def run_ours(args):
     T, M = scn.T, scn.M
     N = args.filters
     prec = q.QEKF_FP64 if args.precision == 64 else q.QEKF_FP32
-    noise = bench_noise(q, first_global_id=rank * N)
+    from quadrotor_landing_b200.sharded import all_reduce_stats, shard_range
+    first_id, n_local = shard_range(N * world, rank, world)     # weak scaling: N filters per GPU
+    assert n_local == N
+    noise = bench_noise(q, first_global_id=first_id)
     if args.no_private_dropout:
         noise.rand_dropout_len = 0
     stride = 200                                   # one statistics sample per simulated second
@@ -224,8 +227,7 @@ def run_ours(args):
         b.stats_reset()
         b.run_monte_carlo_device(shared, noise, 0, T)
         b.copy_stats_device(stats_dev.data_ptr())
-        if dist is not None:
-            dist.all_reduce(stats_dev)
+        all_reduce_stats(stats_dev)                 # NCCL sum over the ranks (no-op at N=1)
         if host_result:
             h_stats[:] = stats_dev.cpu().numpy()
 

@@ -48,6 +48,7 @@ class BatchEKF:
         self._h = C.c_void_p()
         check(self._L.qekf_create(C.byref(self.params), self.N, int(device), int(precision), C.byref(self._h)))
         self.precision = precision
+        self._device = int(device)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -197,6 +198,14 @@ class BatchEKF:
 
     def copy_stats_device(self, dst_ptr: int):
         check(self._L.qekf_copy_stats_device(self._h, C.c_void_p(int(dst_ptr))))
+
+    def stats_tensor(self):
+        """The reduced statistics as a torch tensor on this handle's GPU (what a multi-GPU job all-reduces)."""
+        import torch
+        t = torch.zeros((self._stats_bins, nat.STAT_DIM), dtype=torch.float64, device=torch.device("cuda", self._device))
+        self.copy_stats_device(t.data_ptr())
+        self.sync()
+        return t
 
     # ---- stateless steps ----
     def prediction_step(self, u):

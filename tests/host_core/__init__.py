@@ -6,31 +6,38 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libhost_core.so")
+_LIBS = {64: os.path.join(_HERE, "libhost_core64.so"), 32: os.path.join(_HERE, "libhost_core32.so")}
 _SRC = [os.path.join(_HERE, "host_core.cu")] + [
     os.path.join(_HERE, "..", "..", "quadrotor_landing_b200", "csrc", f)
     for f in ("ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp")
 ]
 
 
+def _build_one(prec):
+    subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-DHC_ONLY_PREC=%d" % prec,
+                    "-Xcompiler", "-fPIC", "-shared", "-o", _LIBS[prec], _SRC[0]], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
 def build(force=False):
-    stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRC)
-    if force or stale:
-        subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
-                        "-Xcompiler", "-fPIC", "-shared", "-o", _LIB, _SRC[0]], check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
-    return _LIB
+    """One library per precision (the instantiation sets are disjoint), compiled in parallel."""
+    todo = [pr for pr, lib_ in _LIBS.items()
+            if force or not os.path.exists(lib_) or any(os.path.getmtime(s) > os.path.getmtime(lib_) for s in _SRC)]
+    if todo:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=2) as ex:
+            list(ex.map(_build_one, todo))
+    return _LIBS[64]
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(prec=64):
+    if prec not in _libs:
         build()
-        _lib = C.CDLL(_LIB)
-    return _lib
+        _libs[prec] = C.CDLL(_LIBS[prec])
+    return _libs[prec]
 
 
 def _dp(a):
@@ -46,7 +53,7 @@ def prediction_step(params, x, P, u, prec=64):
     n = 15 if params.est_bias else 9
     x = _f64(x); P = _f64(P); u = _f64(u)
     xo = np.zeros(16); Po = np.zeros((n, n)); acc = np.zeros(3)
-    lib().hc_prediction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(u), _dp(xo), _dp(Po), _dp(acc))
+    lib(prec).hc_prediction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(u), _dp(xo), _dp(Po), _dp(acc))
     return xo, Po, acc
 
 
@@ -54,7 +61,7 @@ def correction_step(params, x, P, tag, prec=64):
     n = 15 if params.est_bias else 9
     x = _f64(x); P = _f64(P); tag = _f64(tag)
     xo = np.zeros(16); Po = np.zeros((n, n)); obs = np.zeros(7)
-    lib().hc_correction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(tag), _dp(xo), _dp(Po), _dp(obs))
+    lib(prec).hc_correction_step(C.byref(params), int(prec), _dp(x), _dp(P), _dp(tag), _dp(xo), _dp(Po), _dp(obs))
     return xo, Po, obs
 
 
@@ -121,7 +128,7 @@ class HostBatch:
         if tag_valid is not None:
             tag_valid = np.ascontiguousarray(tag_valid, dtype=np.uint8)
             vptr = tag_valid.ctypes.data_as(C.POINTER(C.c_uint8))
-        L = lib()
+        L = lib(self.prec)
         L.hc_run.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.c_int64,
                              C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                              C.POINTER(C.c_uint8), C.c_double] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)] * 2
@@ -140,7 +147,7 @@ class HostBatch:
             vptr = tag_valid.ctypes.data_as(C.POINTER(C.c_uint8))
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         i32 = lambda a: a.ctypes.data_as(ip)
-        L = lib()
+        L = lib(self.prec)
         L.hc_run_ext.argtypes = ([C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp,
                                   C.POINTER(C.c_uint8), C.c_double] + [dp] * 4 + [ip] * 2 + [dp] * 3 + [ip] * 3 +
                                  [C.c_int32, C.c_int32] + [dp] * 5)
@@ -163,7 +170,7 @@ class HostBatch:
         n_steps = scn.T - k0 if n_steps is None else n_steps
         imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
         step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
-        L = lib()
+        L = lib(self.prec)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.hc_run_mc.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, dp,
                                 C.c_void_p, dp, C.c_int32, C.c_int32, C.c_double, dp, dp, dp, dp, ip, ip]

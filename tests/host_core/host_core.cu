@@ -4,6 +4,7 @@
 // tier.  The product library never contains or calls this; on a GPU the same templates run inside
 // run_kernel.
 #include <cmath>
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -238,16 +239,21 @@ template <bool BIAS, bool DIRECT> static void count_t(const qekf_params *p, doub
     out[1] = (double)Cnt::flops;
 }
 
+// Built twice (in parallel): -DHC_ONLY_PREC=64 -> libhost_core64.so, -DHC_ONLY_PREC=32 -> libhost_core32.so.
+#ifndef HC_ONLY_PREC
+#define HC_ONLY_PREC 64
+#endif
+#if HC_ONLY_PREC == 64
+typedef double hc_real;
+#else
+typedef float hc_real;
+#endif
 #define HC_DISPATCH(prec, p, CALL)                                                                  \
     do {                                                                                            \
         const bool b__ = (p)->est_bias != 0, d__ = (p)->direct_orien_method != 0;                   \
-        if ((prec) == 64) {                                                                         \
-            if (b__ && d__) { CALL(double, true, true); } else if (b__) { CALL(double, true, false); } \
-            else if (d__) { CALL(double, false, true); } else { CALL(double, false, false); }       \
-        } else {                                                                                    \
-            if (b__ && d__) { CALL(float, true, true); } else if (b__) { CALL(float, true, false); } \
-            else if (d__) { CALL(float, false, true); } else { CALL(float, false, false); }         \
-        }                                                                                           \
+        if ((prec) != HC_ONLY_PREC) std::abort();                                                   \
+        if (b__ && d__) { CALL(hc_real, true, true); } else if (b__) { CALL(hc_real, true, false); } \
+        else if (d__) { CALL(hc_real, false, true); } else { CALL(hc_real, false, false); }         \
     } while (0)
 
 extern "C" {
