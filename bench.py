@@ -39,7 +39,7 @@ FLOPS = {(1, 1): (1384, 3425), (1, 0): (1384, 3911), (0, 1): (748, 2015), (0, 0)
 STATE_BYTES = (16 + 120) * 8 * 2
 
 
-def bench_params(q):
+def bench_params(q, multirate=False, dynamic=False):
     """rotors.yaml noises (quad_state_estimation/config/relative_pose_EKF_rotors.yaml:13-19) with the
     benchmark rates of SURVEY.md section 8(d): 200 Hz update, 30 Hz tag, gated, single-rate, direct model."""
     p = q.default_params()
@@ -50,8 +50,17 @@ def bench_params(q):
     p.R_r[0], p.R_r[1], p.R_r[2] = 0.015, 0.015, 0.020
     p.R_ang[0], p.R_ang[1], p.R_ang[2] = 0.0015, 0.0015, 0.04
     p.limit_measurement_freq = p.corner_margin_enbl = p.est_bias = p.direct_orien_method = 1
-    p.multirate_ekf = p.dynamic_meas_delay = 0
+    p.multirate_ekf, p.dynamic_meas_delay = int(multirate), int(dynamic)
     return p
+
+
+def bench_scenario(q, p):
+    """The 60 s hover-and-descend landing; with delayed fusion the tag poses arrive 30 ms after capture."""
+    from quadrotor_landing_b200 import scenario
+    spec = scenario.default_spec()
+    if p.multirate_ekf:
+        spec.tag_latency_s = 0.030
+    return scenario.generate(p, spec)
 
 
 def bench_noise(q, first_global_id=0):
@@ -126,8 +135,8 @@ def run_reference(args):
         return
     import quadrotor_landing_b200 as q
     from quadrotor_landing_b200 import scenario
-    p = bench_params(q)
-    scn = scenario.generate(p)          # host-only C++ generator inside libqekf (no GPU needed)
+    p = bench_params(q, args.multirate, args.dynamic_delay)
+    scn = bench_scenario(q, p)          # host-only C++ generator inside libqekf (no GPU needed)
     threads = os.cpu_count() or 1
     sample = max(32, 32 * threads)
     streams = cpu_streams(q, scn, sample)
@@ -149,9 +158,12 @@ def run_reference(args):
 
 
 def workload_config(args, scn):
+    mode = "single-rate"
+    if args.multirate:
+        mode = "delayed-fusion (multirate_ekf, %s delay, 30 ms tag latency)" % ("dynamic" if args.dynamic_delay else "fixed 30 ms")
     return {"workload": "Monte-Carlo replay of a 60 s hover-and-descend landing: %d filters per GPU x %d ticks "
-                        "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), single-rate direct-orientation "
-                        "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T),
+                        "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), %s direct-orientation "
+                        "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T, mode),
             "filters_per_gpu": args.filters, "ticks": int(scn.T), "tag_arrivals": int(scn.M),
             "precision": "fp64" if args.precision == 64 else "fp32",
             "l2": "per-filter state (1.1 GB per 1M filters) is far larger than L2 and is re-read every step; the "
@@ -177,8 +189,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    p = bench_params(q)
-    scn = scenario.generate(p)
+    p = bench_params(q, args.multirate, args.dynamic_delay)
+    scn = bench_scenario(q, p)
     T, M = scn.T, scn.M
     N = args.filters
     prec = q.QEKF_FP64 if args.precision == 64 else q.QEKF_FP32
@@ -352,6 +364,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--multirate", action="store_true", help="delayed-measurement fusion (multirate_ekf) workload")
+    ap.add_argument("--dynamic-delay", action="store_true", help="with --multirate: stamp-derived measurement delay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stats", action="store_true", help="diagnostic: never sample statistics")
     ap.add_argument("--no-private-dropout", action="store_true", help="diagnostic: drop the per-filter dropout window")
