@@ -100,6 +100,13 @@ enum {
 };
 int qekf_set_filter_params(qekf_handle *h, int field, const double *values);
 
+/* The node's parameter file -> qekf_params, as RelativePoseEKFNode's constructor fills the class
+ * (src/relative_pose_EKF_node.cpp:35-136): same keys, same `param<>` defaults for missing scalars, q_vc in
+ * x,y,z,w array order, camera_K row-major, three numbers per tag position.  Reads the flat YAML subset of
+ * config/relative_pose_EKF_{rotors,hardware}.yaml.  Host only (no GPU needed). */
+int qekf_params_from_yaml(const char *path, qekf_params *p);
+int qekf_params_from_yaml_text(const char *text, qekf_params *p);
+
 const char *qekf_last_error_string(void);
 int qekf_num_states(const qekf_handle *h);   /* RelativePoseEKF::num_states (hpp:83) */
 int64_t qekf_num_filters(const qekf_handle *h);

@@ -6,9 +6,10 @@ Python host side: the reference's estimator interface (`RelativePoseEKF`) and th
 if it is not built.
 """
 from ._native import (QEKF_FP32, QEKF_FP64, PF_DELAY, PF_Q, PF_Q_VC, PF_R, PF_R_V_CV, STAT_DIM, QekfError,
-                      QekfNoiseSpec, QekfParams, QekfSharedStreams, default_noise, default_params)
+                      QekfNoiseSpec, QekfParams, QekfSharedStreams, default_noise, default_params,
+                      params_from_yaml, params_from_yaml_text)
 from .ekf import BatchEKF, RelativePoseEKF
 
 __all__ = ["BatchEKF", "RelativePoseEKF", "QekfParams", "QekfError", "default_params", "default_noise",
-           "QekfNoiseSpec", "QekfSharedStreams", "STAT_DIM", "QEKF_FP64", "QEKF_FP32",
+           "QekfNoiseSpec", "QekfSharedStreams", "params_from_yaml", "params_from_yaml_text", "STAT_DIM", "QEKF_FP64", "QEKF_FP32",
            "PF_Q", "PF_R", "PF_R_V_CV", "PF_Q_VC", "PF_DELAY"]

@@ -131,6 +131,7 @@ EXPORTS = [
     "qekf_noise_default", "qekf_run_monte_carlo", "qekf_synthesize_streams", "qekf_stats_configure",
     "qekf_stats_reset", "qekf_get_stats", "qekf_copy_stats_device",
     "qekf_reset_filters", "qekf_launch_count", "qekf_measure_fma_peak", "qekf_step_counts",
+    "qekf_params_from_yaml", "qekf_params_from_yaml_text",
 ]
 
 _lib = None
@@ -187,6 +188,8 @@ def lib() -> C.CDLL:
     L.qekf_launch_count.restype = C.c_int64
     L.qekf_measure_fma_peak.argtypes = [C.c_int, C.c_int, dp]
     L.qekf_step_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+    L.qekf_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(QekfParams)]
+    L.qekf_params_from_yaml_text.argtypes = [C.c_char_p, C.POINTER(QekfParams)]
     _lib = L
     return L
 
@@ -207,6 +210,25 @@ def default_noise() -> QekfNoiseSpec:
     n = QekfNoiseSpec()
     check(lib().qekf_noise_default(C.byref(n)))
     return n
+
+
+PRESET_DIR = os.path.join(HERE, "presets")
+
+
+def params_from_yaml(path: str) -> QekfParams:
+    """The node's parameter file (or the name of a bundled preset: "rotors_sim", "hardware_bundle") -> params,
+    filled as RelativePoseEKFNode's constructor does (relative_pose_EKF_node.cpp:35-136)."""
+    if not os.path.exists(path) and os.path.exists(os.path.join(PRESET_DIR, path + ".yaml")):
+        path = os.path.join(PRESET_DIR, path + ".yaml")
+    p = QekfParams()
+    check(lib().qekf_params_from_yaml(path.encode(), C.byref(p)))
+    return p
+
+
+def params_from_yaml_text(text: str) -> QekfParams:
+    p = QekfParams()
+    check(lib().qekf_params_from_yaml_text(text.encode(), C.byref(p)))
+    return p
 
 
 def default_params() -> QekfParams:

@@ -14,6 +14,7 @@
 
 #include "ekf_params.hpp"
 #include "launch.hpp"
+#include "preset.hpp"
 #include "scenario.hpp"
 
 using namespace qekf;
@@ -394,6 +395,35 @@ int qekf_default_params(qekf_params *p)
     p->est_bias = 1; p->limit_measurement_freq = 0; p->corner_margin_enbl = 1;   // cpp:34-36
     p->direct_orien_method = 0; p->multirate_ekf = 0; p->dynamic_meas_delay = 0; // cpp:37-38, node.cpp:64
     return QEKF_OK;
+}
+
+int qekf_params_from_yaml_text(const char *text, qekf_params *p)
+{
+    if (!text || !p) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    qekf::preset::Doc doc;
+    std::string err = qekf::preset::parse(text, &doc);
+    if (!err.empty()) return fail(QEKF_ERR_BAD_ARG, "parameter file: " + err);
+    qekf_params q;
+    qekf_default_params(&q);
+    err = qekf::preset::apply(doc, &q);
+    if (!err.empty()) return fail(QEKF_ERR_BAD_ARG, "parameter file: " + err);
+    int rc = check_params(&q);
+    if (rc) return rc;
+    *p = q;
+    return QEKF_OK;
+}
+
+int qekf_params_from_yaml(const char *path, qekf_params *p)
+{
+    if (!path || !p) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(QEKF_ERR_BAD_ARG, std::string("cannot open parameter file ") + path);
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    std::fclose(f);
+    return qekf_params_from_yaml_text(text.c_str(), p);
 }
 
 int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precision, qekf_handle **out)
