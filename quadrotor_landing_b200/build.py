@@ -14,6 +14,11 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libqekf.so")
+BIN_DIR = os.path.join(HERE, "bin")
+REPLAY = os.path.join(BIN_DIR, "qekf_replay")
+ROOT = os.path.dirname(HERE)
+REPLAY_SRC = [os.path.join(ROOT, "tools", "replay_driver.cpp"), os.path.join(ROOT, "include", "relative_pose_ekf_gpu.hpp"),
+              os.path.join(ROOT, "include", "qekf.h")]
 HEADERS = ["ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp", "scenario.hpp", "preset.hpp", "launch.hpp",
            os.path.join("..", "..", "include", "qekf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -48,8 +53,22 @@ def _compile(unit, verbose):
     return obj, res.stdout
 
 
+def build_replay_driver(force: bool = False) -> str:
+    """The ROS-free replay driver (C++ host code over the C ABI), linked against the in-tree libqekf.so."""
+    stale = (not os.path.exists(REPLAY)) or any(os.path.getmtime(f) > os.path.getmtime(REPLAY) for f in REPLAY_SRC + [LIB])
+    if force or stale:
+        os.makedirs(BIN_DIR, exist_ok=True)
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), REPLAY_SRC[0], "-L" + LIB_DIR,
+               "-lqekf", "-Wl,-rpath,$ORIGIN/../lib", "-o", REPLAY]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("replay driver build failed:\n" + res.stdout)
+    return REPLAY
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or is_stale()):
+        build_replay_driver(force)
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -63,6 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)
+    build_replay_driver(True)
     return LIB
 
 
