@@ -166,56 +166,87 @@ template <typename T, bool SYNTH> struct Inputs {
 #define QEKF_COLD inline
 #endif
 
-// One statistics sample of one filter after tick k (SYNTH launches: the truth and the true bias are known).
-// Deliberately NOT inlined on the device: it runs once per `stride` ticks and must not take part in the
-// register allocation of the hot loop.
+// One statistics sample after tick k (SYNTH launches: the truth and the true bias are known).  Called by every
+// lane of the CTA at the same point (`valid` = this lane holds an initialised filter that is at the sampling
+// tick), so that the 20 sums can be reduced over the warp with shuffles and leave as ONE atomic per warp and
+// statistic instead of one per lane.  Deliberately NOT inlined on the device: it runs once per `stride` ticks
+// and must not take part in the register allocation of the hot loop.
 template <typename T, bool BIAS, class PS>
-QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> s, PS P, const double *bias)
+QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> s, PS P, const double *bias,
+                            bool valid)
 {
     constexpr int N = PS::n;
     constexpr int NP = N * (N + 1) / 2;
-    const StatsView &sv = a.stats;
-    const int64_t bin = (k + 1) / sv.stride - 1;
-    if (bin < 0 || bin >= sv.n_bins) return;
-    const double *tr = sv.truth + (k + 1) * 10;
-    T e[N];
+    // by value: this function is reached through a generic reference to the kernel parameters, and every store
+    // below would otherwise force the compiler to reload these fields (it cannot rule out aliasing)
+    const StatsView sv = a.stats;
+    const int64_t ld = a.st.ld;
+    T *const __restrict__ gp = a.st.P + i;
+    int32_t bin = (int32_t)((k + 1) / sv.stride - 1);
+    if (bin < 0 || bin >= sv.n_bins) valid = false;
+    double sum[STAT_DIM];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { e[c] = (T)tr[c] - s.r[c]; e[3 + c] = (T)tr[3 + c] - s.v[c]; }
-    {
-        T qt[4] = { (T)tr[6], (T)tr[7], (T)tr[8], (T)tr[9] }, dq[4];
-        quat_conj_mul(s.q, qt, dq);
-        quat_normclip(dq);
-        quat_log(dq, e + 6);
-    }
-    if (BIAS) {
+    for (int c = 0; c < STAT_DIM; ++c) sum[c] = 0.0;
+    if (valid) {
+        const double *tr = sv.truth + (k + 1) * 10;
+        T e[N];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { e[9 + c] = (T)bias[c] - s.ab[c]; e[12 + c] = (T)bias[3 + c] - s.wb[c]; }
-    }
-    // save P, factor in place, restore
-    T *gp = a.st.P + i;
+        for (int c = 0; c < 3; ++c) { e[c] = (T)tr[c] - s.r[c]; e[3 + c] = (T)tr[3 + c] - s.v[c]; }
+        {
+            T qt[4] = { (T)tr[6], (T)tr[7], (T)tr[8], (T)tr[9] }, dq[4];
+            quat_conj_mul(s.q, qt, dq);
+            quat_normclip(dq);
+            quat_log(dq, e + 6);
+        }
+        if (BIAS) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { e[9 + c] = (T)bias[c] - s.ab[c]; e[12 + c] = (T)bias[3 + c] - s.wb[c]; }
+        }
+        // save P, factor in place, restore
+        // (the restore is unrolled deep: with 7 warps per SM nothing else hides its DRAM round trips)
 #pragma unroll 8
-    for (int el = 0; el < NP; ++el) gp[el * a.st.ld] = P.el(el);
-    T nees;
-    bool ok = nees_inplace<T>(P, e, nees);
-#pragma unroll 8
-    for (int el = 0; el < NP; ++el) P.el(el) = gp[el * a.st.ld];
-    double esq = 0;
-    bool finite = true;
+        for (int el = 0; el < NP; ++el) gp[el * ld] = P.el(el);
+        T nees;
+        bool ok = nees_inplace<T>(P, e, nees);
+#pragma unroll 40
+        for (int el = 0; el < NP; ++el) P.el(el) = gp[el * ld];
+        bool finite = true;
 #pragma unroll
-    for (int c = 0; c < N; ++c) { finite = finite && (M<T>::abs_(e[c]) < T(1e30)); }
-    ok = ok && finite && (M<T>::abs_(nees) < T(1e30));
+        for (int c = 0; c < N; ++c) { finite = finite && (M<T>::abs_(e[c]) < T(1e30)); }
+        ok = ok && finite && (M<T>::abs_(nees) < T(1e30));
+        if (ok) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) sum[c] = (double)e[c] * (double)e[c];
+            sum[15] = (double)nees;
+            sum[16] = 1.0;
+            sum[17] = ((double)nees >= sv.chi2_lo && (double)nees <= sv.chi2_hi) ? 1.0 : 0.0;
+            sum[19] = (double)e[0] * (double)e[0] + (double)e[1] * (double)e[1] + (double)e[2] * (double)e[2];
+        } else {
+            sum[18] = 1.0;
+        }
+    }
+#ifdef __CUDA_ARCH__
+    const unsigned full = 0xffffffffu;
+    bin = __reduce_max_sync(full, valid ? bin : -1);          // the valid lanes of a CTA all sit at the same tick
+    if (bin < 0) return;
+#pragma unroll
+    for (int c = 0; c < STAT_DIM; ++c) {
+        double v = sum[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(full, v, off);
+        sum[c] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        double *acc = sv.acc + (((i >> 5) % STAT_REPL) * (int64_t)sv.n_bins + bin) * STAT_DIM;
+#pragma unroll
+        for (int c = 0; c < STAT_DIM; ++c)
+            if (sum[c] != 0.0) atomicAdd(acc + c, sum[c]);
+    }
+#else
+    if (!valid) return;
     double *acc = sv.acc + (((i >> 5) % STAT_REPL) * (int64_t)sv.n_bins + bin) * STAT_DIM;
-    if (ok) {
-#pragma unroll
-        for (int c = 0; c < N; ++c) stat_add(acc + c, (double)e[c] * (double)e[c]);
-        esq = (double)e[0] * (double)e[0] + (double)e[1] * (double)e[1] + (double)e[2] * (double)e[2];
-        stat_add(acc + 15, (double)nees);
-        stat_add(acc + 16, 1.0);
-        if ((double)nees >= sv.chi2_lo && (double)nees <= sv.chi2_hi) stat_add(acc + 17, 1.0);
-        stat_add(acc + 19, esq);
-    } else {
-        stat_add(acc + 18, 1.0);
-    }
+    for (int c = 0; c < STAT_DIM; ++c) acc[c] += sum[c];
+#endif
 }
 
 template <typename T, class PS>
@@ -399,10 +430,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // every lane is at the fence (or finished): sample together, then resume on the next iteration
-            if (at_fence && (flags & FLAG_INIT)) {
-                stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias);
-                ++n_sexec;
-            }
+            const bool mine = live && at_fence && (flags & FLAG_INIT);
+            stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias, mine);
+            if (mine) ++n_sexec;
             at_fence = false;
         }
         bool serve = true;
@@ -609,15 +639,18 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
         if (v.active == 0 && v.at_fence == 0) break;
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
-            if (at_fence && (flags & FLAG_INIT)) {
-                // look at the head: park the checkpoint, replay the nh implied predictions, sample, come back
+            // look at the head: park the checkpoint, replay the nh implied predictions, sample, come back
+            const bool mine = live && at_fence && (flags & FLAG_INIT);
+            Nominal<T> head = s;
+            if (mine) {
                 store_checkpoint<T>(a.st, i, s, P);
                 int32_t first = hpos - nh + 1;
                 if (first < 0) first += L;
-                Nominal<T> head = s;
                 advance_call<T, BIAS>(&head, P, par, ring_i, a.st.ld, L, first, nh, accel);
                 n_pred += (uint32_t)nh;
-                stats_sample<T, BIAS>(a, i, k - 1, head, P, in.bias);
+            }
+            stats_sample<T, BIAS>(a, i, k - 1, head, P, in.bias, mine);
+            if (mine) {
                 load_checkpoint<T>(a.st, i, s, P);
                 ++n_sexec;
             }
