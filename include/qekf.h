@@ -175,7 +175,9 @@ int qekf_correction_step(qekf_handle *h, const double *tag_pose);
  * with counter (index, stream, id), Box-Muller normals.  IMU: u = clean + bias_i + sigma n.  Tag, in the
  * camera frame like the filter's R_k = N R N^T (src/relative_pose_EKF.cpp:462-472): r_c += sigma_p n,
  * q_ct <- exp(sigma_th n) (x) q_ct.  Dropouts: arrivals with dropout_k0 <= tag_step < dropout_k1 are lost
- * for every filter, plus rand_dropout_len ticks starting at a per-filter uniform tick in [lo, hi). */
+ * for every filter, plus rand_dropout_len ticks starting at a per-filter uniform tick in [lo, hi).
+ * Optional detection front-end (edge_loss, range_*): detections are lost when the bundle leaves the image and the
+ * pose noise grows with the camera-to-tag range, instead of a fixed sigma. */
 typedef struct qekf_noise_spec {
     uint64_t seed;
     int64_t first_global_id;     /* global id of this handle's filter 0 (shards of one job share the id space) */
@@ -184,7 +186,13 @@ typedef struct qekf_noise_spec {
     double sigma_tag_pos, sigma_tag_ang;
     int32_t dropout_k0, dropout_k1;
     int32_t rand_dropout_len, rand_dropout_lo, rand_dropout_hi;
-    int32_t reserved;
+    int32_t edge_loss;           /* detection front-end: 1 = an arrival is lost for a filter's realisation when no tag of
+                                    the bundle (tag_widths / tag_positions) projects with all four corners inside the
+                                    camera_width x camera_height image (clean pose, camera_K; the geometry of the
+                                    reference's corner-margin gate, src/relative_pose_EKF.cpp:156-181, at margin 0) */
+    double range_ref;            /* detection front-end: > 0 makes the tag noise range dependent,                  */
+    double range_exp_pos;        /*   sigma_tag_pos * (|r_c_tc| / range_ref)^range_exp_pos                         */
+    double range_exp_ang;        /*   sigma_tag_ang * (|r_c_tc| / range_ref)^range_exp_ang   (0 = as configured)   */
 } qekf_noise_spec;
 
 typedef struct qekf_shared_streams {

@@ -59,9 +59,41 @@ def q_mul(a, b):
                      aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz], axis=-1)
 
 
-def synthesize(noise, imu_clean, tag_step, tag_pose_clean, gids):
+def q_rot(q):
+    """[..., 4] unit quaternions (x, y, z, w) -> [..., 3, 3] rotation matrices."""
+    x, y, z, w = np.moveaxis(q, -1, 0)
+    R = np.empty(q.shape[:-1] + (3, 3))
+    R[..., 0, 0] = 1 - 2 * (y * y + z * z); R[..., 0, 1] = 2 * (x * y - z * w); R[..., 0, 2] = 2 * (x * z + y * w)
+    R[..., 1, 0] = 2 * (x * y + z * w); R[..., 1, 1] = 1 - 2 * (x * x + z * z); R[..., 1, 2] = 2 * (y * z - x * w)
+    R[..., 2, 0] = 2 * (x * z - y * w); R[..., 2, 1] = 2 * (y * z + x * w); R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def bundle_in_image(tag_pose_clean, params):
+    """Detection front-end geometry (include/qekf.h, qekf_noise_spec.edge_loss): [M] bool, true when at least one
+    tag of the bundle projects with all four corners strictly inside the image (clean pose, pinhole camera_K)."""
+    K = np.array(list(params.camera_K)).reshape(3, 3)
+    R = q_rot(tag_pose_clean[:, 3:7])
+    t = tag_pose_clean[:, 0:3]
+    ok = np.zeros(tag_pose_clean.shape[0], dtype=bool)
+    for i in range(params.n_tags):
+        hw = params.tag_widths[i] / 2
+        c0 = np.array([params.tag_positions[3 * i], params.tag_positions[3 * i + 1]])
+        inside = np.ones_like(ok)
+        for sx, sy in ((1, 1), (-1, 1), (-1, -1), (1, -1)):
+            corner = np.array([sx * hw + c0[0], sy * hw + c0[1], 0.0])
+            pc = R @ corner + t
+            u = K[0, 0] * pc[:, 0] / pc[:, 2] + K[0, 1] * pc[:, 1] / pc[:, 2] + K[0, 2]
+            v = K[1, 0] * pc[:, 0] / pc[:, 2] + K[1, 1] * pc[:, 1] / pc[:, 2] + K[1, 2]
+            inside &= (pc[:, 2] > 0) & (u > 0) & (u < params.camera_width) & (v > 0) & (v < params.camera_height)
+        ok |= inside
+    return ok
+
+
+def synthesize(noise, imu_clean, tag_step, tag_pose_clean, gids, params=None):
     """Explicit streams for the given global filter ids, layout of qekf_streams:
-    imu [T][6][n], tag_pose [M][7][n], tag_valid [M][n], bias [6][n].  `noise` has the qekf_noise_spec fields."""
+    imu [T][6][n], tag_pose [M][7][n], tag_valid [M][n], bias [6][n].  `noise` has the qekf_noise_spec fields;
+    `params` (camera + bundle geometry) is needed when the detection front-end is on."""
     gids = np.asarray(gids, dtype=np.int64)
     n = gids.shape[0]
     T, M = imu_clean.shape[0], tag_step.shape[0]
@@ -73,8 +105,16 @@ def synthesize(noise, imu_clean, tag_step, tag_pose_clean, gids):
     imu = imu_clean[:, :, None] + bias[None] + (z * sig).transpose(0, 2, 1)
     zt = normals6(seed, gids[None, :], STREAM_TAG, np.arange(M)[:, None])      # [M, n, 6]
     pose = np.repeat(tag_pose_clean[:, :, None], n, axis=2)
-    pose[:, 0:3] += noise.sigma_tag_pos * zt[:, :, 0:3].transpose(0, 2, 1)
-    v = noise.sigma_tag_ang * zt[:, :, 3:6]
+    sp = np.full(M, noise.sigma_tag_pos)
+    sth = np.full(M, noise.sigma_tag_ang)
+    if getattr(noise, "range_ref", 0.0) > 0:
+        rel = np.linalg.norm(tag_pose_clean[:, 0:3], axis=1) / noise.range_ref
+        if noise.range_exp_pos != 0:
+            sp = sp * rel ** noise.range_exp_pos
+        if noise.range_exp_ang != 0:
+            sth = sth * rel ** noise.range_exp_ang
+    pose[:, 0:3] += sp[:, None, None] * zt[:, :, 0:3].transpose(0, 2, 1)
+    v = sth[:, None, None] * zt[:, :, 3:6]
     nn = np.linalg.norm(v, axis=-1)
     f = np.where(nn < 1e-10, 0.5, np.sin(0.5 * nn) / np.where(nn < 1e-10, 1.0, nn))
     dq = np.concatenate([v * f[..., None], np.cos(0.5 * nn)[..., None]], axis=-1)       # [M, n, 4]
@@ -90,6 +130,8 @@ def synthesize(noise, imu_clean, tag_step, tag_pose_clean, gids):
         span = np.uint64(noise.rand_dropout_hi - noise.rand_dropout_lo)
         start = noise.rand_dropout_lo + ((w[0].astype(np.uint64) * span) >> np.uint64(32)).astype(np.int64)
         valid[(st[:, None] >= start[None]) & (st[:, None] < start[None] + noise.rand_dropout_len)] = 0
+    if getattr(noise, "edge_loss", 0):
+        valid[~bundle_in_image(tag_pose_clean, params)] = 0
     return dict(imu=imu, tag_pose=pose, tag_valid=valid, bias=bias)
 
 

@@ -99,7 +99,8 @@ class QekfNoiseSpec(C.Structure):
         ("sigma_tag_pos", C.c_double), ("sigma_tag_ang", C.c_double),
         ("dropout_k0", C.c_int32), ("dropout_k1", C.c_int32),
         ("rand_dropout_len", C.c_int32), ("rand_dropout_lo", C.c_int32), ("rand_dropout_hi", C.c_int32),
-        ("reserved", C.c_int32),
+        ("edge_loss", C.c_int32),
+        ("range_ref", C.c_double), ("range_exp_pos", C.c_double), ("range_exp_ang", C.c_double),
     ]
 
 

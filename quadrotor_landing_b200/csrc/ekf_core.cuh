@@ -71,6 +71,7 @@ template <typename T> struct Consts {
     T cov_init[5];        // r, v, ang, ab, wb                            (cpp:102-113)
     T Kcam[6];            // camera_K rows 0 and 1
     T u_lo, u_hi, v_lo, v_hi; // width*margin, width*(1-margin), height*margin, height*(1-margin)  (cpp:176-179)
+    T cam_w, cam_h;           // camera_width, camera_height
     T tag_hw[16];         // tag_widths/2
     T tag_px[16], tag_py[16];
     T small_ang_tol;

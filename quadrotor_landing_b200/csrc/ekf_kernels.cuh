@@ -74,6 +74,7 @@ struct StreamView {
     const double *tag_pose;
     const double *tag_stamp;
     const uint8_t *tag_valid;
+    const double *tag_sigma;  // SYNTH with the detection front-end: per-arrival (sigma_p, sigma_th) [M][2], else nullptr
     int64_t cs, is;
     int64_t M;
     int64_t vs;           // stride of tag_valid rows (N)
@@ -90,6 +91,12 @@ template <typename T> struct RunArgs {
     NoiseSpec ns;         // SYNTH launches only
     StatsView stats;      // SYNTH launches only (acc == nullptr: no statistics)
 };
+
+#ifdef __CUDA_ARCH__
+#define QEKF_COLD __device__ __noinline__
+#else
+#define QEKF_COLD inline
+#endif
 
 // Where a filter's inputs come from.  Explicit: per-filter (or shared) streams in memory.  Synth: one
 // clean stream shared by all filters plus this filter's own noise realisation, generated on the fly.
@@ -108,7 +115,7 @@ template <typename T, bool SYNTH> struct Inputs {
         imu_i = a.in.imu + i * a.in.is;
         tag_i = a.in.tag_pose + i * a.in.is;
         cs = a.in.cs;
-        valid_i = a.in.tag_valid ? a.in.tag_valid + i : nullptr;
+        valid_i = (!SYNTH && a.in.tag_valid) ? a.in.tag_valid + i : nullptr;
         vs = a.in.vs;
         ns = &a.ns;
         gid = a.ns.gid0 + i;
@@ -135,36 +142,37 @@ template <typename T, bool SYNTH> struct Inputs {
             for (int cc = 0; cc < 6; ++cc) u[cc] = (T)raw[cc];
         }
     }
-    QEKF_FN void tag_f64(int32_t m, double tag[7]) const
+    // `sv` is the launch's StreamView (kernel-parameter resident): the front-end's shared arrays are read through
+    // it rather than through per-lane copies of the pointers
+    QEKF_FN void tag_f64(const StreamView &sv, int32_t m, double tag[7]) const
     {
         double raw[7];
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) raw[cc] = tag_i[((int64_t)m * 7 + cc) * cs];
-        if (SYNTH) synth_tag(*ns, gid, m, raw, tag);
+        if (SYNTH) {
+            double sp = (double)ns->sig_p, sth = (double)ns->sig_th;
+            if (sv.tag_sigma) { sp = sv.tag_sigma[2 * m]; sth = sv.tag_sigma[2 * m + 1]; }
+            synth_tag(*ns, gid, m, raw, tag, sp, sth);
+        }
         else {
 #pragma unroll
             for (int cc = 0; cc < 7; ++cc) tag[cc] = raw[cc];
         }
     }
-    QEKF_FN void tag(int32_t m, T t[7]) const
+    QEKF_FN void tag(const StreamView &sv, int32_t m, T t[7]) const
     {
         double d[7];
-        tag_f64(m, d);
+        tag_f64(sv, m, d);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) t[cc] = (T)d[cc];
     }
-    QEKF_FN bool valid(int32_t m, int32_t step) const
+    QEKF_FN bool valid(const StreamView &sv, int32_t m, int32_t step) const
     {
-        if (SYNTH) return arrival_valid(*ns, step, priv_start);
+        // SYNTH: sv.tag_valid is the detection front-end's visibility mask [M], shared by all filters (or nullptr)
+        if (SYNTH) return arrival_valid(*ns, step, priv_start) && (sv.tag_valid == nullptr || sv.tag_valid[m] != 0);
         return valid_i ? (valid_i[(int64_t)m * vs] != 0) : true;
     }
 };
-
-#ifdef __CUDA_ARCH__
-#define QEKF_COLD __device__ __noinline__
-#else
-#define QEKF_COLD inline
-#endif
 
 // One statistics sample after tick k (SYNTH launches: the truth and the true bias are known).  Called by every
 // lane of the CTA at the same point (`valid` = this lane holds an initialised filter that is at the sampling
@@ -408,12 +416,12 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176); idempotent ----
         if (active && k == next_tag_step) {
-            if (in.valid(m, (int32_t)k)) {
+            if (in.valid(a.in, m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     T tag0[7];
-                    in.tag(m, tag0);
+                    in.tag(a.in, m, tag0);
                     initialize_state<T, BIAS>(s, P, tag0, par, false);
                     flags |= FLAG_INIT;
                 }
@@ -445,7 +453,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         T tag[7];
         if (exec && want) {
             if (pend_m >= 0) {
-                in.tag(pend_m, tag);
+                in.tag(a.in, pend_m, tag);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
@@ -493,7 +501,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
     // a latched, still unconsumed measurement survives the launch in st.pend
     if ((flags & FLAG_READY) && pend_m >= 0) {
         double tg[7];
-        in.tag_f64(pend_m, tg);
+        in.tag_f64(a.in, pend_m, tg);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
@@ -618,12 +626,12 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
         if (active && k == next_tag_step) {
-            if (in.valid(m, (int32_t)k)) {
+            if (in.valid(a.in, m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     T tag0[7];
-                    in.tag(m, tag0);
+                    in.tag(a.in, m, tag0);
                     initialize_state<T, BIAS>(s, P, tag0, par, false);
                     flags |= FLAG_INIT;
                     nh = 0; hlen = 1;                    // history <- single entry (cpp:326-339)
@@ -668,7 +676,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
         double stamp = 0;
         if (exec && want) {
             if (pend_m >= 0) {
-                in.tag(pend_m, tag);
+                in.tag(a.in, pend_m, tag);
                 stamp = a.in.tag_stamp[pend_m];
             } else {
 #pragma unroll
@@ -737,7 +745,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
 
     if ((flags & FLAG_READY) && pend_m >= 0) {
         double tg[7];
-        in.tag_f64(pend_m, tg);
+        in.tag_f64(a.in, pend_m, tg);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
@@ -902,9 +910,9 @@ __global__ void synth_dump_kernel(RunArgs<T> a, int64_t first, int64_t count, in
     }
     for (int32_t m = 0; m < a.in.M; ++m) {
         double tg[7];
-        in.tag_f64(m, tg);
+        in.tag_f64(a.in, m, tg);
         for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
-        valid_out[(int64_t)m * count + j] = in.valid(m, a.in.tag_step[m]) ? 1 : 0;
+        valid_out[(int64_t)m * count + j] = in.valid(a.in, m, a.in.tag_step[m]) ? 1 : 0;
     }
 }
 

@@ -69,6 +69,8 @@ template <typename T> Consts<T> make_consts(const qekf_params &p)
     c.u_hi = (T)(p.camera_width * (1 - p.tag_in_view_margin));
     c.v_lo = (T)(p.camera_height * p.tag_in_view_margin);
     c.v_hi = (T)(p.camera_height * (1 - p.tag_in_view_margin));
+    c.cam_w = (T)p.camera_width;
+    c.cam_h = (T)p.camera_height;
     c.n_tags = p.n_tags;
     for (int i = 0; i < QEKF_MAX_TAGS; ++i) {
         c.tag_hw[i] = (T)(p.tag_widths[i] / 2);

@@ -11,6 +11,8 @@
 // (relative_pose_EKF.cpp:462-472):  r_c += n_p,  q_ct <- exp(n_th) (x) q_ct.
 #pragma once
 
+#include <cmath>
+
 #include "ekf_core.cuh"
 
 namespace qekf {
@@ -23,6 +25,8 @@ struct NoiseSpec {
     float sig_p, sig_th;          // tag position (m) and attitude (rad) noise
     int32_t drop_k0, drop_k1;     // common dropout: arrivals with k0 <= tag_step < k1 are lost
     int32_t rdrop_len, rdrop_lo, rdrop_hi;   // per-filter dropout of rdrop_len ticks starting in [lo, hi)
+    int32_t edge_loss;            // detection front-end: lose arrivals whose bundle is not entirely in the image
+    double range_ref, range_exp_p, range_exp_th;   // range_ref > 0: sigma * (|r_c| / range_ref)^exp
 };
 
 enum : uint32_t { STREAM_IMU = 0, STREAM_TAG = 2, STREAM_BIAS = 4, STREAM_DROPOUT = 6 };
@@ -121,14 +125,68 @@ QEKF_FN void synth_imu(const NoiseSpec &ns, int64_t gid, int64_t k, const double
     }
 }
 
-// noisy tag pose of arrival m:  r_c + sigma_p n,  exp(sigma_th n) (x) q_ct
-QEKF_FN void synth_tag(const NoiseSpec &ns, int64_t gid, int32_t m, const double clean[7], double tag[7])
+// Detection front-end, geometry: does at least one tag of the bundle project with all four corners strictly inside
+// the image?  Same corner construction and pinhole projection as the reference's corner-margin gate
+// (relative_pose_EKF.cpp:156-181) at margin 0, evaluated in double on the CLEAN pose, so that the set of
+// detections does not depend on the filter's arithmetic type or noise realisation.
+template <typename T> QEKF_FN bool bundle_in_image(const double tag[7], const Consts<T> &c)
+{
+    double R[9];
+    quat_to_rot<double>(tag + 3, R);
+    for (int i = 0; i < c.n_tags; ++i) {
+        const double hw = (double)c.tag_hw[i], px0 = (double)c.tag_px[i], py0 = (double)c.tag_py[i];
+        bool all_in = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double cx = ((k == 0 || k == 3) ? hw : -hw) + px0;
+            const double cy = ((k < 2) ? hw : -hw) + py0;
+            const double p0 = R[0] * cx + R[1] * cy + tag[0];
+            const double p1 = R[3] * cx + R[4] * cy + tag[1];
+            const double p2 = R[6] * cx + R[7] * cy + tag[2];
+            const double iz = 1.0 / p2;
+            const double xn = p0 * iz, yn = p1 * iz;
+            const double uu = (double)c.Kcam[0] * xn + (double)c.Kcam[1] * yn + (double)c.Kcam[2];
+            const double vv = (double)c.Kcam[3] * xn + (double)c.Kcam[4] * yn + (double)c.Kcam[5];
+            all_in = all_in && (p2 > 0.0) && (uu > 0.0) && (uu < (double)c.cam_w) && (vv > 0.0) && (vv < (double)c.cam_h);
+        }
+        if (all_in) return true;
+    }
+    return false;
+}
+
+// The front-end's visibility mask of a whole clean scenario (host): it depends on the clean poses and the camera /
+// bundle geometry only, so it is evaluated once per launch and shared by all filters.
+inline void visibility_mask(const double *tag_pose_clean, int64_t M, const Consts<double> &c, uint8_t *out)
+{
+    for (int64_t m = 0; m < M; ++m) out[m] = bundle_in_image<double>(tag_pose_clean + m * 7, c) ? 1 : 0;
+}
+
+// The front-end's range-dependent tag noise (host): sigma_p, sigma_th of every arrival, [M][2].  Like the
+// visibility mask it depends on the clean poses only and is shared by all filters.
+inline void range_sigmas(const double *tag_pose_clean, int64_t M, const NoiseSpec &ns, double *out)
+{
+    for (int64_t m = 0; m < M; ++m) {
+        const double *c = tag_pose_clean + m * 7;
+        double sp = (double)ns.sig_p, sth = (double)ns.sig_th;
+        if (ns.range_ref > 0.0) {
+            const double rel = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / ns.range_ref;
+            if (ns.range_exp_p != 0.0) sp *= std::pow(rel, ns.range_exp_p);
+            if (ns.range_exp_th != 0.0) sth *= std::pow(rel, ns.range_exp_th);
+        }
+        out[2 * m] = sp;
+        out[2 * m + 1] = sth;
+    }
+}
+
+// noisy tag pose of arrival m:  r_c + sigma_p n,  exp(sigma_th n) (x) q_ct   (sp, sth: this arrival's sigmas)
+QEKF_FN void synth_tag(const NoiseSpec &ns, int64_t gid, int32_t m, const double clean[7], double tag[7], double sp,
+                       double sth)
 {
     float z[6];
     normals6(ns, gid, STREAM_TAG, (uint32_t)m, z);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) tag[i] = clean[i] + (double)ns.sig_p * (double)z[i];
-    double v[3] = { (double)ns.sig_th * (double)z[3], (double)ns.sig_th * (double)z[4], (double)ns.sig_th * (double)z[5] };
+    for (int i = 0; i < 3; ++i) tag[i] = clean[i] + sp * (double)z[i];
+    double v[3] = { sth * (double)z[3], sth * (double)z[4], sth * (double)z[5] };
     double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
     double n = sqrt(n2);
     double f = (n < 1e-10) ? 0.5 : sin(0.5 * n) / n;

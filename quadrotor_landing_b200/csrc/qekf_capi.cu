@@ -77,6 +77,8 @@ struct qekf_handle {
     // cached device copy of the shared clean scenario (qekf_run_monte_carlo with host pointers)
     void *d_shared = nullptr;
     size_t d_shared_bytes = 0;
+    uint8_t *d_mask = nullptr;       // detection front-end visibility mask [M]
+    size_t d_mask_bytes = 0;
     // launch bookkeeping
     int64_t launches = 0;
 };
@@ -122,7 +124,8 @@ int free_state(qekf_handle *h)
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
     cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared); cudaFree(h->counts);
     cudaFree(h->xc); cudaFree(h->Pc); cudaFree(h->ring); cudaFree(h->nh); cudaFree(h->hpos); cudaFree(h->hlen);
-    cudaFree(h->pf); cudaFree(h->pf_delay);
+    cudaFree(h->pf); cudaFree(h->pf_delay); cudaFree(h->d_mask);
+    h->d_mask = nullptr; h->d_mask_bytes = 0;
     h->xc = h->Pc = h->ring = nullptr; h->nh = h->hpos = h->hlen = nullptr; h->ring_len = 0;
     h->pf = nullptr; h->pf_delay = nullptr; h->pf_on = false;
     for (auto &v : h->pf_host) v.clear();
@@ -858,12 +861,14 @@ static NoiseSpec to_device_noise(const qekf_noise_spec &n)
     d.sig_p = (float)n.sigma_tag_pos; d.sig_th = (float)n.sigma_tag_ang;
     d.drop_k0 = n.dropout_k0; d.drop_k1 = n.dropout_k1;
     d.rdrop_len = n.rand_dropout_len; d.rdrop_lo = n.rand_dropout_lo; d.rdrop_hi = n.rand_dropout_hi;
+    d.edge_loss = n.edge_loss;
+    d.range_ref = n.range_ref; d.range_exp_p = n.range_exp_pos; d.range_exp_th = n.range_exp_ang;
     return d;
 }
 
 // Build the kernel's view of a shared clean scenario; host arrays are staged into the handle's slab.
-static int shared_view(qekf_handle *h, const qekf_shared_streams *s, StreamView *in, const double **truth,
-                       std::vector<int32_t> *steps_host)
+static int shared_view(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, StreamView *in,
+                       const double **truth, std::vector<int32_t> *steps_host)
 {
     if (!s->imu_clean || s->T <= 0) return fail(QEKF_ERR_BAD_ARG, "imu_clean is NULL or T <= 0");
     if (s->M < 0 || (s->M > 0 && (!s->tag_step || !s->tag_pose_clean || !s->tag_stamp)))
@@ -881,6 +886,32 @@ static int shared_view(qekf_handle *h, const qekf_shared_streams *s, StreamView 
     std::memset(in, 0, sizeof *in);
     in->cs = 1; in->is = 0; in->M = M; in->vs = 0;
     in->t_start = s->t_start; in->update_freq = h->p.update_freq;
+    // detection front-end: which arrivals see the bundle inside the image, and their range-dependent sigmas (the
+    // same for every filter: evaluated once here, on the clean poses)
+    if ((n->edge_loss || n->range_ref > 0) && M > 0) {
+        std::vector<double> pose((size_t)M * 7);
+        if (s->on_device)
+            CUDA_TRY(cudaMemcpy(pose.data(), s->tag_pose_clean, pose.size() * 8, cudaMemcpyDeviceToHost));
+        else
+            std::memcpy(pose.data(), s->tag_pose_clean, pose.size() * 8);
+        std::vector<double> sig((size_t)M * 2);
+        std::vector<uint8_t> mask((size_t)M, 1);
+        range_sigmas(pose.data(), M, to_device_noise(*n), sig.data());
+        if (n->edge_loss) visibility_mask(pose.data(), M, make_consts<double>(h->p), mask.data());
+        const size_t need = (size_t)M * 16 + (size_t)M;
+        if (need > h->d_mask_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_mask);
+            h->d_mask = nullptr; h->d_mask_bytes = 0;
+            CUDA_TRY(cudaMalloc(&h->d_mask, need));
+            h->d_mask_bytes = need;
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));      // the previous launch may still read these
+        CUDA_TRY(cudaMemcpy(h->d_mask, sig.data(), (size_t)M * 16, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_mask + (size_t)M * 16, mask.data(), (size_t)M, cudaMemcpyHostToDevice));
+        in->tag_sigma = (const double *)h->d_mask;
+        if (n->edge_loss) in->tag_valid = h->d_mask + (size_t)M * 16;
+    }
     if (s->on_device) {
         in->imu = s->imu_clean; in->tag_step = s->tag_step; in->tag_pose = s->tag_pose_clean;
         in->tag_stamp = s->tag_stamp; *truth = s->truth;
@@ -922,7 +953,7 @@ int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qek
     StreamView in;
     const double *truth = nullptr;
     std::vector<int32_t> steps;
-    int rc = shared_view(h, s, &in, &truth, &steps);
+    int rc = shared_view(h, s, n, &in, &truth, &steps);
     if (rc) return rc;
     int32_t m0 = 0;
     for (size_t m = 0; m < steps.size(); ++m)
@@ -941,7 +972,7 @@ int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const 
     StreamView in;
     const double *truth = nullptr;
     std::vector<int32_t> steps;
-    int rc = shared_view(h, s, &in, &truth, &steps);
+    int rc = shared_view(h, s, n, &in, &truth, &steps);
     if (rc) return rc;
     const size_t imu_b = (size_t)s->T * 6 * (size_t)count * 8, tag_b = (size_t)s->M * 7 * (size_t)count * 8;
     const size_t val_b = (size_t)s->M * (size_t)count, bias_b = 6 * (size_t)count * 8;
@@ -952,6 +983,7 @@ int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const 
     RunArgs<double> a;
     std::memset(&a, 0, sizeof a);
     a.in = in;
+    a.c = make_consts<double>(h->p);
     a.ns = to_device_noise(*n);
     CUDA_TRY(launch_dump<double>(a, first, count, s->T, (double *)d, (double *)(d + o_tag), (uint8_t *)(d + o_val),
                                  (double *)(d + o_bias), h->stream));

@@ -194,7 +194,7 @@ class HostBatch:
         return P
 
 
-def synthesize(scn, noise, first, count):
+def synthesize(scn, noise, first, count, params=None):
     """Explicit streams of filters [first, first+count) from the product's generator (host-instantiated)."""
     imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean)
     step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
@@ -203,9 +203,9 @@ def synthesize(scn, noise, first, count):
     o_val = np.zeros((M, count), dtype=np.uint8); o_bias = np.zeros((6, count))
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L = lib()
-    L.hc_synthesize.argtypes = [C.c_void_p, C.c_int64, dp, C.c_int64, ip, dp, C.c_int64, C.c_int64, dp, dp,
+    L.hc_synthesize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, dp, C.c_int64, ip, dp, C.c_int64, C.c_int64, dp, dp,
                                 C.POINTER(C.c_uint8), dp]
-    L.hc_synthesize(C.byref(noise), T, _dp(imu), M, step.ctypes.data_as(ip), _dp(pose), int(first), int(count),
+    L.hc_synthesize(C.byref(params) if params is not None else None, C.byref(noise), T, _dp(imu), M, step.ctypes.data_as(ip), _dp(pose), int(first), int(count),
                     _dp(o_imu), _dp(o_tag), o_val.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(o_bias))
     return dict(imu=o_imu, tag_step=step.copy(), tag_pose=o_tag, tag_stamp=_f64(scn.tag_stamp).copy(), tag_valid=o_val,
                 bias=o_bias)

@@ -140,9 +140,21 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     int32_t m0 = 0;
     while (m0 < M && tag_step[m0] < k0) ++m0;
     a.m0 = m0;
+    std::vector<uint8_t> mask;
+    std::vector<double> sig;
     if (mc && mc->ns) {
         a.in.cs = 1; a.in.is = 0; a.in.vs = 0; a.in.tag_valid = nullptr;
         a.ns = *mc->ns;
+        if (a.ns.edge_loss) {
+            mask.resize((size_t)M);
+            visibility_mask(tag_pose, M, make_consts<double>(*p), mask.data());
+            a.in.tag_valid = mask.data();
+        }
+        if (a.ns.range_ref > 0) {
+            sig.resize((size_t)M * 2);
+            range_sigmas(tag_pose, M, a.ns, sig.data());
+            a.in.tag_sigma = sig.data();
+        }
         if (mc->stats_acc && mc->truth) {
             a.stats.acc = mc->stats_acc; a.stats.truth = mc->truth; a.stats.n_bins = mc->n_bins; a.stats.stride = mc->stride;
             a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
@@ -335,6 +347,7 @@ void hc_run_mc(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_
     ns.sig_p = (float)n->sigma_tag_pos; ns.sig_th = (float)n->sigma_tag_ang;
     ns.drop_k0 = n->dropout_k0; ns.drop_k1 = n->dropout_k1;
     ns.rdrop_len = n->rand_dropout_len; ns.rdrop_lo = n->rand_dropout_lo; ns.rdrop_hi = n->rand_dropout_hi;
+    ns.edge_loss = n->edge_loss; ns.range_ref = n->range_ref; ns.range_exp_p = n->range_exp_pos; ns.range_exp_th = n->range_exp_ang;
     McArgs mc = { &ns, truth, stats_acc, n_bins, stride };
 #define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu_clean, M, tag_step, tag_pose_clean, tag_stamp, nullptr, t_start, x, Ppk, aux, pend, flags, upds, &mc)
     HC_DISPATCH(prec, p, C_);
@@ -342,7 +355,7 @@ void hc_run_mc(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_
 }
 
 // the product's generator, host-instantiated: explicit streams for filters [first, first+count)
-void hc_synthesize(const qekf_noise_spec *n, int64_t T, const double *imu_clean, int64_t M, const int32_t *tag_step,
+void hc_synthesize(const qekf_params *p, const qekf_noise_spec *n, int64_t T, const double *imu_clean, int64_t M, const int32_t *tag_step,
                    const double *tag_pose_clean, int64_t first, int64_t count, double *imu_out, double *tag_out,
                    uint8_t *valid_out, double *bias_out)
 {
@@ -355,6 +368,19 @@ void hc_synthesize(const qekf_noise_spec *n, int64_t T, const double *imu_clean,
     a.ns.sig_p = (float)n->sigma_tag_pos; a.ns.sig_th = (float)n->sigma_tag_ang;
     a.ns.drop_k0 = n->dropout_k0; a.ns.drop_k1 = n->dropout_k1;
     a.ns.rdrop_len = n->rand_dropout_len; a.ns.rdrop_lo = n->rand_dropout_lo; a.ns.rdrop_hi = n->rand_dropout_hi;
+    a.ns.edge_loss = n->edge_loss; a.ns.range_ref = n->range_ref; a.ns.range_exp_p = n->range_exp_pos; a.ns.range_exp_th = n->range_exp_ang;
+    std::vector<uint8_t> mask;
+    std::vector<double> sig;
+    if (p && a.ns.edge_loss) {
+        mask.resize((size_t)M);
+        visibility_mask(tag_pose_clean, M, make_consts<double>(*p), mask.data());
+        a.in.tag_valid = mask.data();
+    }
+    if (a.ns.range_ref > 0) {
+        sig.resize((size_t)M * 2);
+        range_sigmas(tag_pose_clean, M, a.ns, sig.data());
+        a.in.tag_sigma = sig.data();
+    }
     for (int64_t j = 0; j < count; ++j) {
         Inputs<double, true> in;
         in.init(a, first + j);
@@ -367,9 +393,9 @@ void hc_synthesize(const qekf_noise_spec *n, int64_t T, const double *imu_clean,
         }
         for (int32_t m = 0; m < M; ++m) {
             double tg[7];
-            in.tag_f64(m, tg);
+            in.tag_f64(a.in, m, tg);
             for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
-            valid_out[(int64_t)m * count + j] = in.valid(m, tag_step[m]) ? 1 : 0;
+            valid_out[(int64_t)m * count + j] = in.valid(a.in, m, tag_step[m]) ? 1 : 0;
         }
     }
 }
