@@ -315,6 +315,16 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # measured DRAM traffic of this exact launch shape, if an ncu capture of it is on file (profiles/traffic.json)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s|%s|%d|%d" % ("multirate" if args.multirate else "single-rate", "fp64" if prec == q.QEKF_FP64 else "fp32", N, T)
+        if key in tj:
+            traffic = float(tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"])
+            traffic_src = tj[key]["source"].split(":")[0]
+    except Exception:
+        pass
     hbm_bytes = N * STATE_BYTES * (1 if prec == q.QEKF_FP64 else 0.5) + h2d
     line = {
         "metric": "EKF filter-steps/s (propagate+update)", "value": value, "unit": "filter-steps/s",
@@ -327,7 +337,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64" if prec == q.QEKF_FP64 else "fp32", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": traffic_src,
                      "peak_source": "self-measured FMA microbenchmark in this run (qekf_measure_fma_peak); "
                                     "MEASURED_PEAKS.json has no CUDA-core figure",
                      "kernel": "run_kernel", "kernel_ms": k_t * 1e3,
@@ -335,7 +346,8 @@ def run_ours(args):
                      "work": {"prediction_steps": pred_per_launch, "correction_steps": corr_per_launch,
                               "flops_per_prediction": fp, "flops_per_correction": fc}},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_bytes / k_t / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_bytes / k_t / 1e9 / hbm_peak, "traffic": None,
+                         "frac": hbm_bytes / k_t / 1e9 / hbm_peak, "traffic": traffic,
+                         "algorithmic_bytes": hbm_bytes,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "stats": {"rmse_pos_m_final": float(np.sqrt(h_stats[-1, 19] / max(h_stats[-1, 16], 1) / 3)),
                   "mean_nees_final": float(h_stats[-1, 15] / max(h_stats[-1, 16], 1)),
