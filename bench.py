@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 # Floating-point operations executed per call by the structured code (FMA = 2), measured with an
 # instrumented scalar type (tests/host_core hc_count_flops; tests/test_flop_count.py pins these numbers).
 FLOPS = {(1, 1): (1384, 3425), (1, 0): (1384, 3911), (0, 1): (748, 2015), (0, 0): (748, 2231)}
+# FP32 mode: K' = K + (B - K S) S^-1 per gain row: 2 x 36 FMA x (15 | 9) rows
+JOSEPH_EXTRA_FLOPS = {1: 2 * 2 * 36 * 15, 0: 2 * 2 * 36 * 9}
 # Algorithmic HBM bytes per filter-step in Monte-Carlo mode: state + covariance load and store
 # (16 + 120 doubles each way) amortised over the ticks of one launch; the shared clean scenario is L2-resident.
 STATE_BYTES = (16 + 120) * 8 * 2
@@ -303,7 +305,7 @@ def run_ours(args):
     # roofline of the dominant kernel (run_kernel): exact executed work / kernel time
     fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
     if prec == q.QEKF_FP32:
-        fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
+        fc += JOSEPH_EXTRA_FLOPS[int(p.est_bias)]      # the FP32 mode's refined gain (Joseph form), DESIGN.md section 7
     pred_per_launch, corr_per_launch = n_pred / args.steps, n_corr / args.steps
     flops_per_launch = pred_per_launch * fp + corr_per_launch * fc
     k_t = float(np.mean(k_ms)) * 1e-3

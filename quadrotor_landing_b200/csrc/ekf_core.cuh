@@ -50,6 +50,17 @@ template <> struct M<float> {
     static QEKF_FN float min_(float a, float b) { return fminf(a, b); }
 };
 
+// Which covariance update correction_step uses.  The reference computes P^ = (I - K G) P (relative_pose_EKF.cpp:480)
+// and the FP64 path evaluates exactly that.  The FP32 mode uses the Joseph form
+//     P^ = (I - K G) P (I - K G)^T + K R_k K^T = P - K B^T - D K^T,      B = P G^T,  D = B - K S  (the gain's residual).
+// With K = B S^-1 the last term is D S^-1 B^T, so the form is evaluated block by block as P - K' B^T with the
+// refined gain K' = K + D S^-1: if the computed S^-1 is off by a relative E, K is off by E but K' only by E^2 --
+// the property the Joseph form is used for (first-order errors of the gain do not reach the covariance).
+template <typename T> struct UpdateForm { static constexpr bool joseph = false; };
+#ifndef QEKF_NO_JOSEPH      // (defined only by tests/test_core_host.py to measure what the form buys)
+template <> struct UpdateForm<float> { static constexpr bool joseph = true; };
+#endif
+
 // Block indices of the error state: (dr, dv, dtheta, dab, dwb), relative_pose_EKF.cpp:484-485.
 enum { BR = 0, BV = 1, BTH = 2, BAB = 3, BWB = 4 };
 
@@ -619,6 +630,26 @@ template <typename T> QEKF_FN void sym6_inverse(const T s[21], T inv[21])
         }
 }
 
+// Joseph form, one gain row: k <- k + (b - k S) S^-1   (see UpdateForm)
+template <typename T> QEKF_FN void refine_gain_row(const T b[6], const T S[21], const T Sinv[21], T k[6])
+{
+    T d[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        T v = b[m];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) v = M<T>::fma_(-k[l], S[sym_idx<6>(l, m)], v);
+        d[m] = v;
+    }
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        T v = k[m];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) v = M<T>::fma_(d[l], Sinv[sym_idx<6>(l, m)], v);
+        k[m] = v;
+    }
+}
+
 // outputs of a correction that the reference keeps as members (cpp:431,438,443)
 template <typename T> struct Observation {
     T r_t_vt_obs[3];
@@ -640,6 +671,7 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
     constexpr int NB = BIAS ? 5 : 3;
     T dy[6];
     T Sinv[21];
+    T S[21];         // innovation covariance G P G^T + R_k, packed upper triangle
     T Brt[36];       // rows: dr(0..2), dtheta(3..5) of  P_[r,th],. G^T   (6x6)
     T Gam[9];
     {
@@ -741,7 +773,6 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
                     Brt[(3 + a) * 6 + b] = rt[b * 3 + a];
                     Brt[(3 + a) * 6 + 3 + b] = tt[a * 3 + b];
                 }
-            T S[21];
             if (!DIRECT) {
                 // columns 0..2 += (.,th) Gam^T
 #pragma unroll
@@ -803,7 +834,7 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
                 }
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a) {
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 T v = T(0);
@@ -811,6 +842,8 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
                 for (int k = 0; k < 6; ++k) v = M<T>::fma_(Bx[a * 6 + k], Sinv[sym_idx<6>(k, m)], v);
                 Kx[a * 6 + m] = v;
             }
+            if (UpdateForm<T>::joseph) refine_gain_row(Bx + a * 6, S, Sinv, Kx + a * 6);
+        }
         // inject dx_X = K_X dy
         {
             T dx[3];
@@ -889,6 +922,7 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
             for (int l = 0; l < 6; ++l) v = M<T>::fma_(Brt[i * 6 + l], Sinv[sym_idx<6>(l, m)], v);
             k[m] = v;
         }
+        if (UpdateForm<T>::joseph) refine_gain_row(Brt + i * 6, S, Sinv, k);
         T dx = T(0);
 #pragma unroll
         for (int m = 0; m < 6; ++m) dx = M<T>::fma_(k[m], dy[m], dx);

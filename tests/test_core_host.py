@@ -120,3 +120,31 @@ def test_fp32_host_instantiation_is_close():
         xc, Pc = f.correction_step(x, P, tag[:3], tag[3:])
         xh, Ph, _ = hc.correction_step(p, x, P, tag, prec=32)
         assert norm_rel(xh, xc) < 1e-4 and norm_rel(Ph, Pc) < 1e-4
+
+
+def test_fp32_joseph_form_keeps_covariance_positive():
+    """FP32 mode with measurements 1000x sharper than the preset and priors spread over three decades: the
+    Joseph-form update (refined-gain evaluation, ekf_core.cuh UpdateForm) keeps every updated covariance
+    positive-definite and within 3e-6 of the FP64 oracle.  (The plain (I - K G) P form evaluated in FP32 leaves
+    5 of these 300 cases indefinite; measured when the form was introduced)"""
+    rng = np.random.default_rng(3)
+    p = q.default_params()
+    p.direct_orien_method = 1
+    for i in range(3):
+        p.R_r[i] *= 1e-3
+        p.R_ang[i] *= 1e-3
+    f = orc.Filter(orc.params_from(p))
+    qvc = orc.quat_norm(np.array(list(p.q_vc)))
+    errs = []
+    for t in range(300):
+        x, P, u = rand_case(rng, 15, 1)
+        d = 10.0 ** (rng.uniform(-1.5, 1.5, 15) / 2)
+        P = P * np.outer(d, d)
+        qt = orc.quat_mul(x[6:10], orc.quat_exp(rng.normal(scale=0.05, size=3)))
+        q_ct = orc.quat_mul(qt, qvc) * np.array([-1, -1, -1, 1.0])
+        tag = np.concatenate([rng.normal(scale=0.5, size=3) + [0, 0, 2], q_ct])
+        xc, Pc = f.correction_step(x, P, tag[:3], tag[3:])
+        xh, Ph, _ = hc.correction_step(p, x, P, tag, prec=32)
+        assert np.linalg.eigvalsh(Ph).min() > 0
+        errs.append(norm_rel(Ph, Pc))
+    assert max(errs) < 3e-6 and np.median(errs) < 2e-7
