@@ -98,17 +98,6 @@ template <typename T> struct RunArgs {
 #define QEKF_COLD inline
 #endif
 
-// Per-lane scratch in the shared memory the covariance leaves free (element-major like P: slot e of lane l at
-// base[e * stride], conflict-free).  It holds what a correction reports (r_t_vt_obs, q_tv_obs,
-// measurement_delay_curr) until the end of the launch: written straight to their HBM home on every correction
-// these 64 bytes per filter kept getting evicted from L2 (32 GB of DRAM writes per benchmark launch, measured).
-template <typename T> struct ObsScratch {
-    T *base;
-    int stride;
-    QEKF_FN T &at(int e) const { return base[e * stride]; }
-};
-constexpr int OBS_SLOTS = 8;    // aux rows 3..10
-
 // Where a filter's inputs come from.  Explicit: per-filter (or shared) streams in memory.  Synth: one
 // clean stream shared by all filters plus this filter's own noise realisation, generated on the fly.
 template <typename T, bool SYNTH> struct Inputs {
@@ -389,8 +378,7 @@ QEKF_FN CtaVote cta_vote(int *vbuf, uint32_t iter, bool active, bool want, bool 
 // sample together (one execution of the sampling code per stride; the time skew is back to zero).
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
-QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const ObsScratch<T> obs_s, const bool live = true,
-                        int *vbuf = nullptr)
+QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
@@ -408,8 +396,6 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const Ob
         upds = a.st.upds[i];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
-#pragma unroll
-        for (int cc = 0; cc < OBS_SLOTS; ++cc) obs_s.at(cc) = a.st.aux[(3 + cc) * a.st.ld + i];
         in.init(a, i);
         k = a.k0;
         in.raw_imu(k, un);             // software prefetch: un always holds the raw sample of tick k
@@ -493,9 +479,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const Ob
                     s = tmp;
                 }
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) obs_s.at(cc) = obs.r_t_vt_obs[cc];
+                for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) obs_s.at(3 + cc) = obs.q_tv_obs[cc];
+                for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
                 upds = 0;
                 flags |= FLAG_CORRECTED;
             } else {
@@ -536,8 +522,6 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const Ob
     }
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
-#pragma unroll
-    for (int cc = 0; cc < OBS_SLOTS; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs_s.at(cc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -601,8 +585,7 @@ QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_
 // (tag dropout, rejected detection) catch their checkpoint up to size-D inside their CTA-mates' correction
 // events, where the warp executes prediction code anyway.
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
-QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const ObsScratch<T> obs_s, const bool live = true,
-                           int *vbuf = nullptr)
+QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
@@ -623,8 +606,6 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
         nh = a.st.nh[i]; hpos = a.st.hpos[i]; hlen = a.st.hlen[i];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
-#pragma unroll
-        for (int cc = 0; cc < OBS_SLOTS; ++cc) obs_s.at(cc) = a.st.aux[(3 + cc) * a.st.ld + i];
         in.init(a, i);
         k = a.k0;
         in.raw_imu(k, un);
@@ -720,7 +701,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
             if (ind < 0) ind = 0;
             n_adv = ind - (hlen - 1 - nh);               // >= 0 by the ring invariant
             if (n_adv < 0) n_adv = 0;
-            obs_s.at(7) = (T)delay;                      // measurement_delay_curr
+            a.st.aux[10 * a.st.ld + i] = (T)delay;       // measurement_delay_curr
         } else if ((flags & FLAG_INIT) && active && (event || (exec && nh >= L - 1))) {
             n_adv = (nh > Dm1) ? nh - Dm1 : 0;           // catch-up (never past entry size-D)
         }
@@ -737,9 +718,9 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
             Observation<T> obs;
             correction_call<T, BIAS, DIRECT>(&s, P, tag, par, &obs);
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) obs_s.at(cc) = obs.r_t_vt_obs[cc];
+            for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) obs_s.at(3 + cc) = obs.q_tv_obs[cc];
+            for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
             hlen = nh + 1;                               // history before the corrected entry is erased (cpp:214-219)
         }
         if (exec) {
@@ -795,8 +776,6 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
     }
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
-#pragma unroll
-    for (int cc = 0; cc < OBS_SLOTS; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs_s.at(cc);
 }
 
 // fused multi-tick replay: MR = false single-rate filter, MR = true delayed-measurement fusion
@@ -810,12 +789,10 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4) ? 2 : 1) run_kernel(co
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
-    T *after_p = sm + (size_t)BLOCK * (N * (N + 1) / 2);
-    const ObsScratch<T> obs_s{ after_p + threadIdx.x, BLOCK };
-    int *vbuf = reinterpret_cast<int *>(after_p + (size_t)BLOCK * OBS_SLOTS);
+    int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
     // padding lanes still take part in the votes
-    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, obs_s, i < a.st.n, vbuf);
-    else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, obs_s, i < a.st.n, vbuf);
+    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
+    else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -98,11 +98,7 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     return s;
 }
 
-// covariance + correction-report scratch + vote words (run_kernel's layout; the single-step kernels use the front only)
-size_t smem_bytes(const qekf_handle *h)
-{
-    return (size_t)BLOCK * (h->np + OBS_SLOTS) * h->tsize + VOTE_WORDS * sizeof(int);
-}
+size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize + VOTE_WORDS * sizeof(int); }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
 
 // dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision

@@ -194,12 +194,10 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     const bool synth = mc && mc->ns;
     for (int64_t i = 0; i < N; ++i) {
         PLocal<T, NS> P;
-        T obs_store[OBS_SLOTS];
-        const ObsScratch<T> obs_s{ obs_store, 1 };
 #define RUN_(S, F)                                                         \
         do {                                                               \
-            if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P, obs_s);  \
-            else run_filter<T, BIAS, DIRECT, S, F>(a, i, P, obs_s);        \
+            if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P);         \
+            else run_filter<T, BIAS, DIRECT, S, F>(a, i, P);               \
         } while (0)
         if (synth && pf) RUN_(true, true);
         else if (synth) RUN_(true, false);
