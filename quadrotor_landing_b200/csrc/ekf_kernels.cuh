@@ -527,6 +527,23 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 // ------------------------------------------------------------------------------------------------
 // delayed-measurement fusion (multirate_ekf = true), evaluated lazily
 // ------------------------------------------------------------------------------------------------
+// An int32 that lives in the lane's slot of a shared-memory scratch array.  The multirate loop calls three
+// out-of-line functions per iteration; everything that is live across a call ends up in local memory (the ABI
+// keeps few registers across calls), and with 7 warps per SM the L2 round trips of those reloads sat on the
+// critical path of every light tick (73 local loads per warp-tick, long-scoreboard 2.9 per issue).  The
+// sequencer's integer state is therefore kept here explicitly: a shared-memory access costs a tenth of that.
+struct SmemInt {
+    int32_t *p;
+    QEKF_FN operator int32_t() const { return *p; }
+    QEKF_FN SmemInt &operator=(int32_t v) { *p = v; return *this; }
+    QEKF_FN SmemInt &operator=(const SmemInt &o) { *p = *o.p; return *this; }   // assigns the value, not the slot
+    QEKF_FN SmemInt &operator+=(int32_t v) { *p += v; return *this; }
+    QEKF_FN SmemInt &operator-=(int32_t v) { *p -= v; return *this; }
+    QEKF_FN SmemInt &operator|=(int32_t v) { *p |= v; return *this; }
+    QEKF_FN SmemInt &operator&=(int32_t v) { *p &= v; return *this; }
+    QEKF_FN SmemInt &operator++() { *p += 1; return *this; }
+};
+constexpr int MR_SCRATCH_INTS = 16;   // flags upds nh hpos hlen m next_tag_step pend_m held k | 6 floats: the true bias' normals
 template <typename T, class PS>
 QEKF_FN void load_checkpoint(const DeviceState<T> &st, int64_t i, Nominal<T> &s, PS &P)
 {
@@ -585,7 +602,8 @@ QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_
 // (tag dropout, rejected detection) catch their checkpoint up to size-D inside their CTA-mates' correction
 // events, where the warp executes prediction code anyway.
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
-QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
+QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
+                           const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
@@ -594,11 +612,14 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
     const int32_t L = a.st.ring_len, Dm1 = a.st.dmax_m1;
     T *ring_i = a.st.ring + i;
     Nominal<T> s;                      // the checkpoint
-    int32_t flags = 0, upds = 0, nh = 0, hpos = 0, hlen = 0;
+    SmemInt flags{ scr + 0 * scr_stride }, upds{ scr + 1 * scr_stride }, nh{ scr + 2 * scr_stride };
+    SmemInt hpos{ scr + 3 * scr_stride }, hlen{ scr + 4 * scr_stride }, m{ scr + 5 * scr_stride };
+    SmemInt next_tag_step{ scr + 6 * scr_stride }, pend_m{ scr + 7 * scr_stride }, held{ scr + 8 * scr_stride };
+    SmemInt k{ scr + 9 * scr_stride };       // tick index (qekf_run bounds it to int32)
+    flags = 0; upds = 0; nh = 0; hpos = 0; hlen = 0;
     T accel[3] = { T(0), T(0), T(0) };
     Inputs<T, SYNTH> in;
-    double un[6] = { 0, 0, 0, 0, 0, 0 };
-    int64_t k = k_end;
+    k = (int32_t)k_end;
     if (live) {
         load_checkpoint<T>(a.st, i, s, P);
         flags = a.st.flags[i];
@@ -607,15 +628,25 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
         in.init(a, i);
-        k = a.k0;
-        in.raw_imu(k, un);
+        k = (int32_t)a.k0;
+        if (SYNTH) {                   // the true bias as its six normals, in the scratch (12 registers less across calls)
+            float z[6];
+            normals6(a.ns, in.gid, STREAM_BIAS, 0u, z);
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) reinterpret_cast<float *>(scr)[(10 + cc) * scr_stride] = z[cc];
+        }
     }
+    auto true_bias_now = [&](double b[6]) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc)
+            b[cc] = (double)(cc < 3 ? a.ns.sig_ba : a.ns.sig_bw) * (double)reinterpret_cast<const float *>(scr)[(10 + cc) * scr_stride];
+    };
 
     uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0;
-    int32_t m = a.m0;
-    int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
-    int32_t pend_m = -1;
-    int32_t held = 0;
+    m = a.m0;
+    next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+    pend_m = -1;
+    held = 0;
     bool at_fence = false;
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
@@ -657,7 +688,9 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
                 advance_call<T, BIAS>(&head, P, par, ring_i, a.st.ld, L, first, nh, accel);
                 n_pred += (uint32_t)nh;
             }
-            stats_sample<T, BIAS>(a, i, k - 1, head, P, in.bias, mine);
+            double tb[6] = { 0, 0, 0, 0, 0, 0 };
+            if (SYNTH) true_bias_now(tb);
+            stats_sample<T, BIAS>(a, i, k - 1, head, P, tb, mine);
             if (mine) {
                 load_checkpoint<T>(a.st, i, s, P);
                 ++n_sexec;
@@ -725,8 +758,22 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
         }
         if (exec) {
             // cpp:240-257: the head prediction is implied; its input joins the history
+            // (the raw sample is fetched here rather than prefetched across iterations: whatever is carried across the
+            // out-of-line calls of this loop lives in local memory, and nothing on the control path waits for this load)
             T u[6];
-            in.imu(k, un, u);
+            {
+                double un[6];
+                in.raw_imu(k, un);
+                if (SYNTH) {
+                    double tb[6], ud[6];
+                    true_bias_now(tb);
+                    synth_imu(a.ns, in.gid, k, un, tb, ud);
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
+                } else {
+                    in.imu(k, un, u);
+                }
+            }
             hpos = (hpos + 1 == L) ? 0 : hpos + 1;
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) ring_i[((int64_t)hpos * 6 + cc) * a.st.ld] = u[cc];
@@ -737,7 +784,6 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, const
         }
         if (active && !(want && !serve)) {
             ++k;
-            if (k < k_end) in.raw_imu(k, un);
             if (do_stats && (k % a.stats.stride) == 0) at_fence = true;
         }
     }
@@ -791,8 +837,16 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4) ? 2 : 1) run_kernel(co
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
     // padding lanes still take part in the votes
-    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
-    else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
+    if (MR) {
+        if (sizeof(T) == 8) {       // FP64: the sequencer's integers live in the shared memory behind the vote words
+            run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, i < a.st.n, vbuf);
+        } else {                    // FP32: two CTAs share the SM and leave no room for it
+            int32_t own[MR_SCRATCH_INTS];
+            run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, own, 1, i < a.st.n, vbuf);
+        }
+    } else {
+        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

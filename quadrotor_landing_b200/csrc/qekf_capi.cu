@@ -98,7 +98,12 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     return s;
 }
 
-size_t smem_bytes(const qekf_handle *h) { return (size_t)BLOCK * h->np * h->tsize + VOTE_WORDS * sizeof(int); }
+size_t smem_bytes(const qekf_handle *h)
+{
+    size_t b = (size_t)BLOCK * h->np * h->tsize + VOTE_WORDS * sizeof(int);
+    if (h->p.multirate_ekf && h->precision == QEKF_FP64) b += (size_t)BLOCK * MR_SCRATCH_INTS * sizeof(int32_t);
+    return b;
+}
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
 
 // dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision
