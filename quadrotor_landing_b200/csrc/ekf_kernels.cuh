@@ -129,6 +129,11 @@ template <typename T, bool SYNTH> struct Inputs {
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) u[cc] = imu_i[(k * 6 + cc) * cs];
     }
+    QEKF_FN void raw_imu(const StreamView &sv, int64_t k, double u[6]) const
+    {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) u[cc] = SYNTH ? sv.imu[k * 6 + cc] : imu_i[(k * 6 + cc) * cs];
+    }
     // turn the raw (prefetched) sample of tick k into what the filter sees
     QEKF_FN void imu(int64_t k, const double raw[6], T u[6]) const
     {
@@ -147,8 +152,10 @@ template <typename T, bool SYNTH> struct Inputs {
     QEKF_FN void tag_f64(const StreamView &sv, int32_t m, double tag[7]) const
     {
         double raw[7];
+        // SYNTH launches read the one shared clean scenario (element stride 1) straight through the kernel
+        // parameters: no per-lane pointer has to stay alive for it
 #pragma unroll
-        for (int cc = 0; cc < 7; ++cc) raw[cc] = tag_i[((int64_t)m * 7 + cc) * cs];
+        for (int cc = 0; cc < 7; ++cc) raw[cc] = SYNTH ? sv.tag_pose[(int64_t)m * 7 + cc] : tag_i[((int64_t)m * 7 + cc) * cs];
         if (SYNTH) {
             double sp = (double)ns->sig_p, sth = (double)ns->sig_th;
             if (sv.tag_sigma) { sp = sv.tag_sigma[2 * m]; sth = sv.tag_sigma[2 * m + 1]; }
@@ -763,7 +770,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
             T u[6];
             {
                 double un[6];
-                in.raw_imu(k, un);
+                in.raw_imu(a.in, k, un);
                 if (SYNTH) {
                     double tb[6], ud[6];
                     true_bias_now(tb);
