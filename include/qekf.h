@@ -85,12 +85,18 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
 int qekf_destroy(qekf_handle *h);
 
 /* Overwrite parameters and re-run initialize_params() (node.cpp:53-138 then :138).  Like the
- * reference this resets cov_pert to cov_init but keeps the nominal state. */
+ * reference this resets cov_pert to cov_init but keeps the nominal state.  With multirate_ekf the delayed-fusion
+ * history restarts from the current estimate (the reference keeps its old history vectors, so its next delayed
+ * correction would silently discard the covariance reset).  Changing est_bias re-allocates the filters and drops
+ * per-filter overrides. */
 int qekf_set_params(qekf_handle *h, const qekf_params *p);
 int qekf_get_params(const qekf_handle *h, qekf_params *p);
 
 /* Per-filter parameter overrides for sweeps (no reference equivalent: the reference has one
- * filter).  values is a HOST array [dim][N]; must be called before the first run. */
+ * filter).  values is a HOST array [dim][N].  Each filter's derived quantities are recomputed exactly as
+ * initialize_params() would (src/relative_pose_EKF.cpp:87-125); fields never overridden keep the handle-wide
+ * value.  Meant to be called before the first run; with multirate_ekf a QEKF_PF_DELAY override that changes the
+ * largest step delay restarts the delayed-fusion histories from the current estimates. */
 enum {
     QEKF_PF_Q = 0,      /* dim 12: Q_a, Q_w, Q_ab, Q_wb */
     QEKF_PF_R = 1,      /* dim 6 : R_r, R_ang */
@@ -125,7 +131,10 @@ int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3]);
 int qekf_set_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp);
 /* RelativePoseEKF::initialize_state(bool) (src/relative_pose_EKF.cpp:305-344). */
 int qekf_initialize_state(qekf_handle *h, int reinit_bias);
-/* RelativePoseEKF::filter_update(double) (src/relative_pose_EKF.cpp:127-303): one tick. */
+/* RelativePoseEKF::filter_update(double) (src/relative_pose_EKF.cpp:127-303): one tick, single-rate or with
+ * delayed-measurement fusion (multirate_ekf, fixed or dynamic delay: cpp:196-264).  The x_hist / u_hist / P_hist
+ * vectors of the reference are kept as a lagged checkpoint plus a ring of IMU inputs and re-evaluated on demand;
+ * what the accessors return after the call is what the reference's members would hold. */
 int qekf_filter_update(qekf_handle *h, double t_curr);
 
 /* ---- batch replay: filter_update iterated n_steps times inside one kernel launch -------------- */
