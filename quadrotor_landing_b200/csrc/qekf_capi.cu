@@ -643,6 +643,7 @@ int qekf_run(qekf_handle *h, const qekf_streams *s, int64_t k0, int64_t n_steps)
     if (!h || !s) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return QEKF_OK;
     if (k0 < 0 || n_steps < 0 || k0 + n_steps > s->T) return fail(QEKF_ERR_BAD_ARG, "tick range outside the stream");
+    if (k0 + n_steps > 2147483647LL) return fail(QEKF_ERR_BAD_ARG, "tick indices are limited to 31 bits (as tag_step is)");
     if (!s->imu) return fail(QEKF_ERR_BAD_ARG, "imu stream is NULL");
     if (s->M < 0 || (s->M > 0 && (!s->tag_step || !s->tag_pose || !s->tag_stamp)))
         return fail(QEKF_ERR_BAD_ARG, "tag streams are NULL");
@@ -954,6 +955,7 @@ int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qek
     if (!h || !s || !n) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return QEKF_OK;
     if (k0 < 0 || n_steps < 0 || k0 + n_steps > s->T) return fail(QEKF_ERR_BAD_ARG, "tick range outside the stream");
+    if (k0 + n_steps > 2147483647LL) return fail(QEKF_ERR_BAD_ARG, "tick indices are limited to 31 bits (as tag_step is)");
     CUDA_TRY(cudaSetDevice(h->device));
     StreamView in;
     const double *truth = nullptr;
