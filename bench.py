@@ -189,6 +189,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) out of it
+        os.environ["NCCL_DEBUG"] = os.environ.get("QEKF_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     p = bench_params(q, args.multirate, args.dynamic_delay)
