@@ -408,7 +408,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         in.raw_imu(k, un);             // software prefetch: un always holds the raw sample of tick k
     }
 
-    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_cexec = 0, n_sexec = 0;
+    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0;
     int32_t m = a.m0;
     int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     int32_t pend_m = -1;               // index of the latched arrival; -1 = latched pose lives in st.pend
@@ -469,7 +469,6 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
             perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
             held = 0;
         }
-        if (perform) ++n_cexec;
 
         if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
             // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----

@@ -209,15 +209,6 @@ struct StatsView {
     double chi2_lo, chi2_hi;
 };
 
-QEKF_FN void stat_add(double *addr, double v)
-{
-#ifdef __CUDA_ARCH__
-    atomicAdd(addr, v);
-#else
-    *addr += v;
-#endif
-}
-
 // NEES = e^T P^-1 e by an in-place packed Cholesky P = U^T U carried out IN the covariance storage (row j
 // of U overwrites row j of P), with e carried along as an extra right-hand-side column.  The caller must
 // have saved P elsewhere and must restore it afterwards.  The outer (row) loop and the dot products over
