@@ -73,6 +73,23 @@ def bench_noise(q, first_global_id=0):
     return n
 
 
+def apply_sweep(q, b, p, N, seed):
+    """BASELINE config 5: every filter gets its own process / measurement noise and camera extrinsic."""
+    rng = np.random.default_rng(seed)
+    base_q = np.array(list(p.Q_a) + list(p.Q_w) + list(p.Q_ab) + list(p.Q_wb))
+    base_r = np.array(list(p.R_r) + list(p.R_ang))
+    b.set_filter_params(q.PF_Q, base_q[:, None] * 10 ** rng.uniform(-1, 1, size=(12, N)))
+    b.set_filter_params(q.PF_R, base_r[:, None] * 10 ** rng.uniform(-1, 1, size=(6, N)))
+    b.set_filter_params(q.PF_R_V_CV, np.array(list(p.r_v_cv))[:, None] + rng.uniform(-0.02, 0.02, size=(3, N)))
+    ang = rng.normal(scale=np.deg2rad(1.0) / 2, size=(3, N))                 # small rotation about a random axis
+    dq = np.concatenate([ang, np.sqrt(1 - (ang ** 2).sum(axis=0))[None]])   # x, y, z, w
+    qv = np.array(list(p.q_vc))
+    x1, y1, z1, w1 = qv[:, None] * np.ones((4, N))
+    x2, y2, z2, w2 = dq
+    b.set_filter_params(q.PF_Q_VC, np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                                             w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]))
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -161,8 +178,11 @@ def run_reference(args):
 
 def workload_config(args, scn):
     mode = "single-rate"
+    if getattr(args, "sweep", False):
+        mode = "per-filter Q/R/camera-extrinsic sweep, " + mode
     if args.multirate:
-        mode = "delayed-fusion (multirate_ekf, %s delay, 30 ms tag latency)" % ("dynamic" if args.dynamic_delay else "fixed 30 ms")
+        mode = mode.replace("single-rate", "") + "delayed-fusion (multirate_ekf, %s delay, 30 ms tag latency)" % (
+            "dynamic" if args.dynamic_delay else "fixed 30 ms")
     return {"workload": "Monte-Carlo replay of a 60 s hover-and-descend landing: %d filters per GPU x %d ticks "
                         "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), %s direct-orientation "
                         "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T, mode),
@@ -210,6 +230,8 @@ def run_ours(args):
     b = q.BatchEKF(p, N, device=local, precision=prec)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
+    if args.sweep:
+        apply_sweep(q, b, p, N, seed=1234 + rank)
     b.stats_configure(nb, stride if not args.no_stats else 10 ** 9)
     stats_dev = torch.zeros((nb, q.STAT_DIM), dtype=torch.float64, device=dev)
 
@@ -382,6 +404,9 @@ def main():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--multirate", action="store_true", help="delayed-measurement fusion (multirate_ekf) workload")
     ap.add_argument("--dynamic-delay", action="store_true", help="with --multirate: stamp-derived measurement delay")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE config 5: per-filter Q / R within x[0.1, 10] of the preset (log-uniform), camera extrinsic "
+                         "+-2 cm / +-1 deg (use with --multirate --dynamic-delay)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stats", action="store_true", help="diagnostic: never sample statistics")
     ap.add_argument("--no-private-dropout", action="store_true", help="diagnostic: drop the per-filter dropout window")
