@@ -53,3 +53,28 @@ def test_full_size_monte_carlo(N, windows):
     # spot check of the whole batch: finite everywhere (state is 134 MB at 1M filters)
     assert np.isfinite(b.state()).all()
     b.close()
+
+
+def test_full_size_fp32_mode():
+    """BASELINE config 3, FP32 mode: 1,048,576 filters x 12,000 ticks in FP32 (Joseph-form update, two CTAs per SM).
+    Every filter sampled every second, nothing diverged, windows of the id range within 1e-4 of FP64 handles that
+    own exactly those global ids, their covariances symmetric positive-definite."""
+    p = bench.bench_params(q)
+    scn = scenario.generate(p)
+    noise = bench.bench_noise(q)
+    N, stride = 1 << 20, 200
+    nb = scn.T // stride
+    b = q.BatchEKF(p, N, precision=q.QEKF_FP32)
+    b.stats_configure(nb, stride)
+    b.run_monte_carlo(scn, noise)
+    stats = b.stats()
+    assert np.array_equal(stats[:, 16], np.full(nb, float(N))) and stats[:, 18].sum() == 0
+    for first, count in [(0, 64), (777777, 64), (N - 64, 64)]:
+        ref = q.BatchEKF(p, count)
+        nz = bench.bench_noise(q, first_global_id=first)
+        ref.run_monte_carlo(scn, nz)
+        x32, P32 = b.state(first, count), b.cov(first, count)
+        assert norm_rel(x32, ref.state()) < 1e-4 and norm_rel(P32, ref.cov()) < 1e-4
+        assert np.all(np.linalg.eigvalsh(P32.transpose(2, 0, 1)) > 0)
+        ref.close()
+    b.close()
