@@ -831,10 +831,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 }
 
 // fused multi-tick replay: MR = false single-rate filter, MR = true delayed-measurement fusion
-// FP32: a filter's covariance takes 480 B of shared memory, so two CTAs share an SM (14 warps) and the register
-// budget is capped accordingly; FP64: 960 B per filter, one CTA (7 warps) fills the SM.
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4) ? 2 : 1) run_kernel(const __grid_constant__ RunArgs<T> a)
+__global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ RunArgs<T> a)
 {
     constexpr int N = BIAS ? 15 : 9;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -846,7 +844,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4) ? 2 : 1) run_kernel(co
     if (MR) {
         if (sizeof(T) == 8) {       // FP64: the sequencer's integers live in the shared memory behind the vote words
             run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, i < a.st.n, vbuf);
-        } else {                    // FP32: two CTAs share the SM and leave no room for it
+        } else {                    // FP32: 448 covariances leave no room for it
             int32_t own[MR_SCRATCH_INTS];
             run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, own, 1, i < a.st.n, vbuf);
         }

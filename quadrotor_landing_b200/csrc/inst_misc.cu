@@ -7,10 +7,10 @@ template <typename T, bool BIAS, bool PF>
 cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
                            int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = deliver_tag_kernel<T, BIAS, PF, BLOCK>;
+    auto kern = deliver_tag_kernel<T, BIAS, PF, BlockOf<T>::value>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, BLOCK, smem, stream>>>(st, c, pose8, force_init, reinit_bias);
+    kern<<<grid, BlockOf<T>::value, smem, stream>>>(st, c, pose8, force_init, reinit_bias);
     return cudaGetLastError();
 }
 
@@ -18,10 +18,10 @@ template <typename T, bool BIAS, bool PF>
 cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,
                            cudaStream_t stream)
 {
-    auto kern = predict_kernel<T, BIAS, PF, BLOCK>;
+    auto kern = predict_kernel<T, BIAS, PF, BlockOf<T>::value>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, BLOCK, smem, stream>>>(st, c, u);
+    kern<<<grid, BlockOf<T>::value, smem, stream>>>(st, c, u);
     return cudaGetLastError();
 }
 
@@ -29,10 +29,10 @@ template <typename T, bool BIAS, bool DIRECT, bool PF>
 cudaError_t launch_correct(const DeviceState<T> &st, const Consts<T> &c, const double *tag, unsigned grid, size_t smem,
                            cudaStream_t stream)
 {
-    auto kern = correct_kernel<T, BIAS, DIRECT, PF, BLOCK>;
+    auto kern = correct_kernel<T, BIAS, DIRECT, PF, BlockOf<T>::value>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, BLOCK, smem, stream>>>(st, c, tag);
+    kern<<<grid, BlockOf<T>::value, smem, stream>>>(st, c, tag);
     return cudaGetLastError();
 }
 

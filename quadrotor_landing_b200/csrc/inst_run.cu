@@ -8,10 +8,10 @@ namespace qekf {
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = run_kernel<T, BIAS, DIRECT, SYNTH, MR, PF, BLOCK>;
+    auto kern = run_kernel<T, BIAS, DIRECT, SYNTH, MR, PF, BlockOf<T>::value>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, BLOCK, smem, stream>>>(a);
+    kern<<<grid, BlockOf<T>::value, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -8,7 +8,10 @@
 
 namespace qekf {
 
-constexpr int BLOCK = 224;  // 7 warps: 7 x 30 KB of FP64 covariance fill one SM's shared memory (1 CTA / SM)
+// One CTA per SM, filled by the covariances: FP64 7 warps x 30 KB, FP32 14 warps x 15 KB (a single 448-thread CTA
+// rather than two independent 224-thread ones: in lockstep its warps share one instruction stream, two CTAs drift
+// apart and thrash the instruction cache -- no_instruction 1.0 per issue in profiles/r1_13_fp32.md).
+template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 448 : 224; };
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);

@@ -98,13 +98,14 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     return s;
 }
 
+int block_of(const qekf_handle *h) { return h->precision == QEKF_FP64 ? BlockOf<double>::value : BlockOf<float>::value; }
 size_t smem_bytes(const qekf_handle *h)
 {
-    size_t b = (size_t)BLOCK * h->np * h->tsize + VOTE_WORDS * sizeof(int);
-    if (h->p.multirate_ekf && h->precision == QEKF_FP64) b += (size_t)BLOCK * MR_SCRATCH_INTS * sizeof(int32_t);
+    size_t b = (size_t)block_of(h) * h->np * h->tsize + VOTE_WORDS * sizeof(int);
+    if (h->p.multirate_ekf && h->precision == QEKF_FP64) b += (size_t)block_of(h) * MR_SCRATCH_INTS * sizeof(int32_t);
     return b;
 }
-unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + BLOCK - 1) / BLOCK); }
+unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + block_of(h) - 1) / block_of(h)); }
 
 // dispatch over the code-shape flags (est_bias, direct_orien_method) and the precision
 #define QEKF_DISPATCH(h, CALL)                                                             \
