@@ -842,12 +842,8 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
     // padding lanes still take part in the votes
     if (MR) {
-        if (sizeof(T) == 8) {       // FP64: the sequencer's integers live in the shared memory behind the vote words
-            run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, i < a.st.n, vbuf);
-        } else {                    // FP32: 448 covariances leave no room for it
-            int32_t own[MR_SCRATCH_INTS];
-            run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, own, 1, i < a.st.n, vbuf);
-        }
+        // the sequencer's integers live in the shared memory behind the vote words
+        run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, i < a.st.n, vbuf);
     } else {
         run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
     }

@@ -8,10 +8,11 @@
 
 namespace qekf {
 
-// One CTA per SM, filled by the covariances: FP64 7 warps x 30 KB, FP32 14 warps x 15 KB (a single 448-thread CTA
-// rather than two independent 224-thread ones: in lockstep its warps share one instruction stream, two CTAs drift
-// apart and thrash the instruction cache -- no_instruction 1.0 per issue in profiles/r1_13_fp32.md).
-template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 448 : 224; };
+// One CTA per SM.  FP64: 7 warps x 30 KB of covariance fill the shared memory.  FP32: shared memory would hold 14
+// warps, but the register file decides: 12 warps at 168 registers beat 14 at 128 by 17 % (and 8 at 255, which
+// does not spill at all, is as fast as 12); one lockstep CTA rather than two independent 224-thread ones, which
+// drift apart and thrash the instruction cache (no_instruction 1.0 per issue in profiles/r1_13_fp32.md).
+template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 384 : 224; };
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);

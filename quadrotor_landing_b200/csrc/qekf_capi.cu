@@ -102,7 +102,7 @@ int block_of(const qekf_handle *h) { return h->precision == QEKF_FP64 ? BlockOf<
 size_t smem_bytes(const qekf_handle *h)
 {
     size_t b = (size_t)block_of(h) * h->np * h->tsize + VOTE_WORDS * sizeof(int);
-    if (h->p.multirate_ekf && h->precision == QEKF_FP64) b += (size_t)block_of(h) * MR_SCRATCH_INTS * sizeof(int32_t);
+    if (h->p.multirate_ekf) b += (size_t)block_of(h) * MR_SCRATCH_INTS * sizeof(int32_t);
     return b;
 }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + block_of(h) - 1) / block_of(h)); }
