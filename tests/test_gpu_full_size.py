@@ -78,3 +78,29 @@ def test_full_size_fp32_mode():
         assert np.all(np.linalg.eigvalsh(P32.transpose(2, 0, 1)) > 0)
         ref.close()
     b.close()
+
+
+def test_full_size_delayed_fusion():
+    """Delayed-measurement fusion at scale: 262,144 filters x 12,000 ticks, dynamic delay, 30 ms tag latency.
+    Windows of the id range against the oracle (which keeps the reference's full history vectors), the whole batch
+    through the statistics."""
+    p = bench.bench_params(q, multirate=True, dynamic=True)
+    scn = bench.bench_scenario(q, p)
+    noise = bench.bench_noise(q)
+    N, stride = 1 << 18, 200
+    nb = scn.T // stride
+    b = q.BatchEKF(p, N)
+    b.stats_configure(nb, stride)
+    b.run_monte_carlo(scn, noise, 0, 7001)
+    b.run_monte_carlo(scn, noise, 7001, scn.T - 7001)
+    stats = b.stats()
+    assert np.array_equal(stats[:, 16], np.full(nb, float(N))) and stats[:, 18].sum() == 0
+    for first, count in [(0, 48), (N // 2 + 5, 32), (N - 48, 48)]:
+        st = b.synthesize_streams(scn, noise, first, count)
+        ob = orc.Batch(orc.params_from(p), count)
+        ob.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        assert norm_rel(b.state(first, count), ob.state()) < TOL and norm_rel(b.cov(first, count), ob.cov()) < TOL
+        assert np.array_equal(b.flags(first, count), ob.flags())          # incl. x_hist.size()
+    npred, ncorr = b.step_counts()
+    assert npred < 1.15 * N * scn.T                                      # lazily evaluated history: ~1.08 predictions per tick
+    b.close()
