@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 # Floating-point operations executed per call by the structured code (FMA = 2), measured with an
 # instrumented scalar type (tests/host_core hc_count_flops; tests/test_flop_count.py pins these numbers).
-FLOPS = {(1, 1): (1384, 3425), (1, 0): (1384, 3911), (0, 1): (748, 2015), (0, 0): (748, 2231)}
+FLOPS = {(1, 1): (1398, 3425), (1, 0): (1398, 3911), (0, 1): (762, 2015), (0, 0): (762, 2231)}
 # FP32 mode: K' = K + (B - K S) S^-1 per gain row: 2 x 36 FMA x (15 | 9) rows
 JOSEPH_EXTRA_FLOPS = {1: 2 * 2 * 36 * 15, 0: 2 * 2 * 36 * 9}
 # Algorithmic HBM bytes per filter-step in Monte-Carlo mode: state + covariance load and store

@@ -309,6 +309,91 @@ template <typename T> QEKF_FN void quat_log(const T q[4], T v[3])
 }
 
 // ------------------------------------------------------------------------------------------------
+// attitude propagation of one tick                           relative_pose_EKF.cpp:383-401
+//   q <- normclip(q (x) exp(dth)),   Phi = I - skew(dth)  (|dth| < small_ang_tol)  or  Rodrigues(-|dth|, dth/|dth|)
+// returned as Phi = cs I + s1 K1 + s2 dth dth^T with K1 = -skew(dth).
+//
+// Fast path (|dth| < 0.2 rad per tick, i.e. < 40 rad/s at 200 Hz): sin(h)/|dth| and cos(h), h = |dth|/2, are
+// even series in |dth|^2, so there is no square root, no division and no sincos on the per-tick dependency
+// chain; sin(ang)/ang = 2 f ch and (1 - cos ang)/ang^2 = 2 f^2 follow from the half-angle values.  exp(dth) is
+// a unit quaternion to rounding (the reference's normalisation of it changes the last bit only) and the
+// product of two unit quaternions is renormalised with one Newton step of 1/sqrt about 1 (error 3/8 e^2,
+// e = |q|^2 - 1 ~ 1e-16).  Anything else (large rates, a nominal quaternion that is not unit) takes the
+// reference's literal sequence in attitude_step_exact.  Both agree to ~1e-16; the parity bar is 1e-9.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct PhiCoef { T cs, s1, s2; };
+
+template <typename T> __host__ __device__ __noinline__ void attitude_step_exact(T q[4], const T dth[3], T small_ang_tol, PhiCoef<T> &pc)
+{
+    T qe[4], ang, sh, ch;
+    quat_exp(dth, qe, ang, sh, ch);
+    T qn[4];
+    quat_mul(q, qe, qn);
+    quat_normclip(qn);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = qn[i];
+    if (ang < small_ang_tol) {
+        pc.cs = T(1); pc.s1 = T(1); pc.s2 = T(0);
+    } else {
+        const T inv = T(1) / ang;
+        pc.s1 = T(2) * sh * ch * inv;
+        pc.s2 = T(2) * sh * sh * inv * inv;
+        pc.cs = T(1) - T(2) * sh * sh;
+    }
+}
+
+template <typename T> QEKF_FN void attitude_step(T q[4], const T dth[3], T small_ang_tol, PhiCoef<T> &pc)
+{
+    const T n2 = M<T>::fma_(dth[2], dth[2], M<T>::fma_(dth[1], dth[1], dth[0] * dth[0]));
+    if (n2 < T(0.04)) {
+        const T x = T(0.25) * n2;                      // h^2
+        T sc = M<T>::fma_(x, T(-1.0 / 110.0), T(1));   // sin(h)/h = 1 - x/6 (1 - x/20 (1 - x/42 (1 - x/72 (1 - x/110))))
+        sc = M<T>::fma_(-x * sc, T(1.0 / 72.0), T(1));
+        sc = M<T>::fma_(-x * sc, T(1.0 / 42.0), T(1));
+        sc = M<T>::fma_(-x * sc, T(1.0 / 20.0), T(1));
+        sc = M<T>::fma_(-x * sc, T(1.0 / 6.0), T(1));
+        T ch = M<T>::fma_(x, T(-1.0 / 132.0), T(1));   // cos(h) = 1 - x/2 (1 - x/12 (1 - x/30 (1 - x/56 (1 - x/90 (1 - x/132)))))
+        ch = M<T>::fma_(-x * ch, T(1.0 / 90.0), T(1));
+        ch = M<T>::fma_(-x * ch, T(1.0 / 56.0), T(1));
+        ch = M<T>::fma_(-x * ch, T(1.0 / 30.0), T(1));
+        ch = M<T>::fma_(-x * ch, T(1.0 / 12.0), T(1));
+        ch = M<T>::fma_(-x * ch, T(0.5), T(1));
+        const T f = T(0.5) * sc;                       // sin(h)/|dth|
+        const T qe[4] = { dth[0] * f, dth[1] * f, dth[2] * f, ch };
+        T qn[4];
+        quat_mul(q, qe, qn);
+        const T m2 = M<T>::fma_(qn[3], qn[3], M<T>::fma_(qn[2], qn[2], M<T>::fma_(qn[1], qn[1], qn[0] * qn[0])));
+        const T e = m2 - T(1);
+        if (M<T>::abs_(e) < T(1e-8)) {
+            T sc2 = M<T>::fma_(T(-0.5), e, T(1));
+            if (qn[3] < T(-0.75)) sc2 = -sc2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = qn[i] * sc2;
+            const bool small = n2 < small_ang_tol * small_ang_tol && small_ang_tol > T(0);
+            const T f2 = T(2) * f;
+            pc.s1 = small ? T(1) : f2 * ch;
+            pc.s2 = small ? T(0) : f2 * f;
+            pc.cs = small ? T(1) : M<T>::fma_(-f2 * f, n2, T(1));
+            return;
+        }
+    }
+    attitude_step_exact(q, dth, small_ang_tol, pc);
+}
+
+// Phi (row-major) from its coefficients
+template <typename T> QEKF_FN void phi_matrix(const PhiCoef<T> &pc, const T dth[3], T Phi[9])
+{
+    const T a0 = pc.s2 * dth[0], a1 = pc.s2 * dth[1], a2 = pc.s2 * dth[2];
+    const T b0 = pc.s1 * dth[0], b1 = pc.s1 * dth[1], b2 = pc.s1 * dth[2];
+    Phi[0] = M<T>::fma_(a0, dth[0], pc.cs);
+    Phi[4] = M<T>::fma_(a1, dth[1], pc.cs);
+    Phi[8] = M<T>::fma_(a2, dth[2], pc.cs);
+    Phi[1] = M<T>::fma_(a0, dth[1], b2);  Phi[3] = M<T>::fma_(a0, dth[1], -b2);
+    Phi[2] = M<T>::fma_(a0, dth[2], -b1); Phi[6] = M<T>::fma_(a0, dth[2], b1);
+    Phi[5] = M<T>::fma_(a1, dth[2], b0);  Phi[7] = M<T>::fma_(a1, dth[2], -b0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // initialize_state                                              relative_pose_EKF.cpp:305-344
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool BIAS, class PS, class PAR>
@@ -397,33 +482,9 @@ QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par,
         }
         // attitude: q <- normclip(q (x) exp(dT w)); Phi = I - skew(dT w) or Rodrigues(-|dT w|)
         T dth[3] = { d * w[0], d * w[1], d * w[2] };
-        T qe[4], ang, sh, ch;
-        quat_exp(dth, qe, ang, sh, ch);
-        T qn[4];
-        quat_mul(s.q, qe, qn);
-        quat_normclip(qn);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s.q[i] = qn[i];
-        if (ang < c.small_ang_tol) {
-            Phi[0] = T(1);    Phi[1] = dth[2];  Phi[2] = -dth[1];
-            Phi[3] = -dth[2]; Phi[4] = T(1);    Phi[5] = dth[0];
-            Phi[6] = dth[1];  Phi[7] = -dth[0]; Phi[8] = T(1);
-        } else {
-            T inv = T(1) / ang;
-            T n0 = dth[0] * inv, n1 = dth[1] * inv, n2 = dth[2] * inv;
-            T sn = T(2) * sh * ch;            // sin(ang)
-            T omc = T(2) * sh * sh;           // 1 - cos(ang)
-            T cs = T(1) - omc;                // cos(ang)
-            T c0 = omc * n0, c1 = omc * n1, c2 = omc * n2;
-            T t;
-            // Rodrigues for angle -ang about n (sin(-ang) = -sn)
-            t = c0 * n1; Phi[1] = t + sn * n2; Phi[3] = t - sn * n2;
-            t = c0 * n2; Phi[2] = t - sn * n1; Phi[6] = t + sn * n1;
-            t = c1 * n2; Phi[5] = t + sn * n0; Phi[7] = t - sn * n0;
-            Phi[0] = M<T>::fma_(c0, n0, cs);
-            Phi[4] = M<T>::fma_(c1, n1, cs);
-            Phi[8] = M<T>::fma_(c2, n2, cs);
-        }
+        PhiCoef<T> pc;
+        attitude_step(s.q, dth, c.small_ang_tol, pc);
+        phi_matrix(pc, dth, Phi);
     }
 
     // ---- E1: dr += dT dv -------------------------------------------------------------------
@@ -665,6 +726,97 @@ template <typename T> struct Observation {
 // i.e. exactly  P^ = (I - K G) P  and  dx = K dy  without materialising K or I - K G.
 // JOSEPH selects the symmetrised Joseph form used by the FP32 mode.
 // ------------------------------------------------------------------------------------------------
+// The measurement-model part of correction_step (cpp:417-472): observed pose, innovation dy, R_k = N R N^T
+// (packed upper 6x6) and, for the conventional model, Gam = C skew(C^T r).  Needs the nominal attitude and
+// position only; shared by the thread-per-filter update below and the cooperative one (ekf_coop.cuh).
+template <typename T, bool DIRECT, class PAR>
+QEKF_FN void correction_front(const T q[4], const T r[3], const T tag[7], const PAR &par, Observation<T> &obs, T dy[6],
+                              T Rk[21], T Gam[9])
+{
+    T C[9];
+    quat_to_rot(q, C);
+    {
+        T qq[4], qvc[4] = { par.q_vc(0), par.q_vc(1), par.q_vc(2), par.q_vc(3) };
+        quat_mul(qvc, tag + 3, qq);
+        obs.q_tv_obs[0] = -qq[0]; obs.q_tv_obs[1] = -qq[1]; obs.q_tv_obs[2] = -qq[2]; obs.q_tv_obs[3] = qq[3];
+        quat_normclip(obs.q_tv_obs);
+    }
+    {
+        T pc[3], ro[3], Cvc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Cvc[i] = par.C_vc(i);
+        mv(Cvc, tag, pc);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pc[i] += par.r_v_cv(i);
+        if (DIRECT) {
+            T Ro[9];
+            quat_to_rot(obs.q_tv_obs, Ro);
+            mv(Ro, pc, ro);
+        } else {
+            mv(C, pc, ro);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { obs.r_t_vt_obs[i] = -ro[i]; dy[i] = obs.r_t_vt_obs[i] - r[i]; }
+    }
+    {
+        T dq[4];
+        quat_conj_mul(q, obs.q_tv_obs, dq);
+        quat_normclip(dq);
+        quat_log(dq, dy + 3);
+    }
+    // R_k = N R N^T, packed upper 6x6
+    {
+        // (0,0) block: C RC C^T  (+ skew(r) diag(Ra) skew(r)^T for the direct model)
+        const T rc1 = par.RC(1), rc2 = par.RC(2), rc4 = par.RC(4);
+        T RCf[9] = { par.RC(0), rc1, rc2, rc1, par.RC(3), rc4, rc2, rc4, par.RC(5) };
+        T t[9], r00[9];
+        mm_set(t, C, RCf);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) r00[i] = T(0);
+        mmt_acc(r00, t, C);
+        if (DIRECT) {
+            const T rx = r[0], ry = r[1], rz = r[2];
+            const T a0 = par.Ra(0), a1 = par.Ra(1), a2 = par.Ra(2);
+            // skew(r) diag(a) skew(r)^T
+            r00[0] += a1 * rz * rz + a2 * ry * ry;
+            r00[1] += -a2 * rx * ry;
+            r00[2] += -a1 * rx * rz;
+            r00[4] += a0 * rz * rz + a2 * rx * rx;
+            r00[5] += -a0 * ry * rz;
+            r00[8] += a0 * ry * ry + a1 * rx * rx;
+            // (0,1) block: skew(r) D
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const T d0 = par.D(0 + j), d1 = par.D(3 + j), d2 = par.D(6 + j);
+                Rk[sym_idx<6>(0, 3 + j)] = -rz * d1 + ry * d2;
+                Rk[sym_idx<6>(1, 3 + j)] = rz * d0 - rx * d2;
+                Rk[sym_idx<6>(2, 3 + j)] = -ry * d0 + rx * d1;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Rk[sym_idx<6>(i, 3 + j)] = T(0);
+        }
+        Rk[sym_idx<6>(0, 0)] = r00[0]; Rk[sym_idx<6>(0, 1)] = r00[1]; Rk[sym_idx<6>(0, 2)] = r00[2];
+        Rk[sym_idx<6>(1, 1)] = r00[4]; Rk[sym_idx<6>(1, 2)] = r00[5]; Rk[sym_idx<6>(2, 2)] = r00[8];
+        Rk[sym_idx<6>(3, 3)] = par.RA(0); Rk[sym_idx<6>(3, 4)] = par.RA(1); Rk[sym_idx<6>(3, 5)] = par.RA(2);
+        Rk[sym_idx<6>(4, 4)] = par.RA(3); Rk[sym_idx<6>(4, 5)] = par.RA(4); Rk[sym_idx<6>(5, 5)] = par.RA(5);
+    }
+    if (!DIRECT) {
+        // Gam = C skew(C^T r)
+        T Ctr[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Ctr[i] = C[0 * 3 + i] * r[0] + C[1 * 3 + i] * r[1] + C[2 * 3 + i] * r[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Gam[i * 3 + 0] = C[i * 3 + 1] * Ctr[2] - C[i * 3 + 2] * Ctr[1];
+            Gam[i * 3 + 1] = C[i * 3 + 2] * Ctr[0] - C[i * 3 + 0] * Ctr[2];
+            Gam[i * 3 + 2] = C[i * 3 + 0] * Ctr[1] - C[i * 3 + 1] * Ctr[0];
+        }
+    }
+}
+
 template <typename T, bool BIAS, bool DIRECT, class PS, class PAR>
 QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &par, Observation<T> &obs)
 {
@@ -675,89 +827,8 @@ QEKF_FN void correction_step(Nominal<T> &s, PS &P, const T tag[7], const PAR &pa
     T Brt[36];       // rows: dr(0..2), dtheta(3..5) of  P_[r,th],. G^T   (6x6)
     T Gam[9];
     {
-        T C[9];
-        quat_to_rot(s.q, C);
-        {
-            T qq[4], qvc[4] = { par.q_vc(0), par.q_vc(1), par.q_vc(2), par.q_vc(3) };
-            quat_mul(qvc, tag + 3, qq);
-            obs.q_tv_obs[0] = -qq[0]; obs.q_tv_obs[1] = -qq[1]; obs.q_tv_obs[2] = -qq[2]; obs.q_tv_obs[3] = qq[3];
-            quat_normclip(obs.q_tv_obs);
-        }
-        {
-            T pc[3], ro[3], Cvc[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Cvc[i] = par.C_vc(i);
-            mv(Cvc, tag, pc);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) pc[i] += par.r_v_cv(i);
-            if (DIRECT) {
-                T Ro[9];
-                quat_to_rot(obs.q_tv_obs, Ro);
-                mv(Ro, pc, ro);
-            } else {
-                mv(C, pc, ro);
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { obs.r_t_vt_obs[i] = -ro[i]; dy[i] = obs.r_t_vt_obs[i] - s.r[i]; }
-        }
-        {
-            T dq[4];
-            quat_conj_mul(s.q, obs.q_tv_obs, dq);
-            quat_normclip(dq);
-            quat_log(dq, dy + 3);
-        }
-        // R_k = N R N^T, packed upper 6x6
         T Rk[21];
-        {
-            // (0,0) block: C RC C^T  (+ skew(r) diag(Ra) skew(r)^T for the direct model)
-            const T rc1 = par.RC(1), rc2 = par.RC(2), rc4 = par.RC(4);
-            T RCf[9] = { par.RC(0), rc1, rc2, rc1, par.RC(3), rc4, rc2, rc4, par.RC(5) };
-            T t[9], r00[9];
-            mm_set(t, C, RCf);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) r00[i] = T(0);
-            mmt_acc(r00, t, C);
-            if (DIRECT) {
-                const T rx = s.r[0], ry = s.r[1], rz = s.r[2];
-                const T a0 = par.Ra(0), a1 = par.Ra(1), a2 = par.Ra(2);
-                // skew(r) diag(a) skew(r)^T
-                r00[0] += a1 * rz * rz + a2 * ry * ry;
-                r00[1] += -a2 * rx * ry;
-                r00[2] += -a1 * rx * rz;
-                r00[4] += a0 * rz * rz + a2 * rx * rx;
-                r00[5] += -a0 * ry * rz;
-                r00[8] += a0 * ry * ry + a1 * rx * rx;
-                // (0,1) block: skew(r) D
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const T d0 = par.D(0 + j), d1 = par.D(3 + j), d2 = par.D(6 + j);
-                    Rk[sym_idx<6>(0, 3 + j)] = -rz * d1 + ry * d2;
-                    Rk[sym_idx<6>(1, 3 + j)] = rz * d0 - rx * d2;
-                    Rk[sym_idx<6>(2, 3 + j)] = -ry * d0 + rx * d1;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) Rk[sym_idx<6>(i, 3 + j)] = T(0);
-            }
-            Rk[sym_idx<6>(0, 0)] = r00[0]; Rk[sym_idx<6>(0, 1)] = r00[1]; Rk[sym_idx<6>(0, 2)] = r00[2];
-            Rk[sym_idx<6>(1, 1)] = r00[4]; Rk[sym_idx<6>(1, 2)] = r00[5]; Rk[sym_idx<6>(2, 2)] = r00[8];
-            Rk[sym_idx<6>(3, 3)] = par.RA(0); Rk[sym_idx<6>(3, 4)] = par.RA(1); Rk[sym_idx<6>(3, 5)] = par.RA(2);
-            Rk[sym_idx<6>(4, 4)] = par.RA(3); Rk[sym_idx<6>(4, 5)] = par.RA(4); Rk[sym_idx<6>(5, 5)] = par.RA(5);
-        }
-        if (!DIRECT) {
-            // Gam = C skew(C^T r)
-            T Ctr[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) Ctr[i] = C[0 * 3 + i] * s.r[0] + C[1 * 3 + i] * s.r[1] + C[2 * 3 + i] * s.r[2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                Gam[i * 3 + 0] = C[i * 3 + 1] * Ctr[2] - C[i * 3 + 2] * Ctr[1];
-                Gam[i * 3 + 1] = C[i * 3 + 2] * Ctr[0] - C[i * 3 + 0] * Ctr[2];
-                Gam[i * 3 + 2] = C[i * 3 + 0] * Ctr[1] - C[i * 3 + 1] * Ctr[0];
-            }
-        }
+        correction_front<T, DIRECT>(s.q, s.r, tag, par, obs, dy, Rk, Gam);
         // Brt = P_[r,th],. G^T  and  S = G Brt + R_k
         {
             T rr[9], rt[9], tt[9];
