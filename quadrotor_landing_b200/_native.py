@@ -125,7 +125,7 @@ STAT_DIM = 20
 EXPORTS = [
     "qekf_default_params", "qekf_create", "qekf_destroy", "qekf_set_params", "qekf_get_params",
     "qekf_set_filter_params", "qekf_last_error_string", "qekf_num_states", "qekf_num_filters",
-    "qekf_set_stream", "qekf_sync", "qekf_set_imu", "qekf_set_tag", "qekf_initialize_state",
+    "qekf_set_mapping", "qekf_set_stream", "qekf_sync", "qekf_set_imu", "qekf_set_tag", "qekf_initialize_state",
     "qekf_filter_update", "qekf_run", "qekf_get_state", "qekf_get_cov", "qekf_get_aux", "qekf_get_flags",
     "qekf_set_state", "qekf_prediction_step", "qekf_correction_step",
     "qekf_scenario_default", "qekf_scenario_sizes", "qekf_scenario_generate",
@@ -158,6 +158,7 @@ def lib() -> C.CDLL:
     L.qekf_num_states.argtypes = [vp]
     L.qekf_num_filters.argtypes = [vp]
     L.qekf_num_filters.restype = C.c_int64
+    L.qekf_set_mapping.argtypes = [vp, C.c_int, C.c_int]
     L.qekf_set_stream.argtypes = [vp, vp]
     L.qekf_sync.argtypes = [vp]
     L.qekf_set_imu.argtypes = [vp, dp, dp]

@@ -20,12 +20,17 @@ ROOT = os.path.dirname(HERE)
 REPLAY_SRC = [os.path.join(ROOT, "tools", "replay_driver.cpp"), os.path.join(ROOT, "include", "relative_pose_ekf_gpu.hpp"),
               os.path.join(ROOT, "include", "qekf.h")]
 HEADERS = ["ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp", "scenario.hpp", "preset.hpp", "launch.hpp",
-           os.path.join("..", "..", "include", "qekf.h")]
+           "launch_coop.hpp", os.path.join("..", "..", "include", "qekf.h")]
+COOP_HEADERS = ["ekf_coop.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _units():
     units = [("qekf_capi", "qekf_capi.cu", []), ("inst_misc", "inst_misc.cu", [])]
+    # the cooperative kernel's units first: the benchmark variant (b1 d1 s1) is the longest compile
+    for b, d, sy in ((1, 1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, 1, 1), (0, 1, 0), (0, 0, 1), (0, 0, 0)):
+        units.append(("inst_coop_b%d_d%d_s%d" % (b, d, sy), "inst_coop.cu",
+                      ["-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d, "-DQ_SYNTH=%d" % sy]))
     for t in ("double", "float"):
         for b in (1, 0):
             for d in (1, 0):
@@ -39,13 +44,20 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = HEADERS + ["qekf_capi.cu", "inst_misc.cu", "inst_run.cu"]
+    srcs = HEADERS + COOP_HEADERS + ["qekf_capi.cu", "inst_misc.cu", "inst_run.cu", "inst_coop.cu"]
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in srcs)
 
 
-def _compile(unit, verbose):
+def _deps(src):
+    return [src] + HEADERS + (COOP_HEADERS if src == "inst_coop.cu" else [])
+
+
+def _compile(unit, verbose, force=False):
     name, src, defs = unit
     obj = os.path.join(OBJ_DIR, name + ".o")
+    if not force and not verbose and os.path.exists(obj) and all(
+            os.path.getmtime(os.path.join(CSRC, f)) <= os.path.getmtime(obj) for f in _deps(src)):
+        return obj, ""          # up to date: only units whose sources changed are recompiled
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
@@ -73,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(10, os.cpu_count() or 4)) as ex:
-        results = list(ex.map(lambda u: _compile(u, verbose), _units()))
+        results = list(ex.map(lambda u: _compile(u, verbose, force), _units()))
     objs = [r[0] for r in results]
     if verbose:
         for r in results:

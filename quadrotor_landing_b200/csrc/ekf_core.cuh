@@ -377,7 +377,15 @@ template <typename T> QEKF_FN void attitude_step(T q[4], const T dth[3], T small
             return;
         }
     }
-    attitude_step_exact(q, dth, small_ang_tol, pc);
+    {   // (copies: the out-of-line call must not pin the caller's q / coefficients to local memory)
+        T qq[4] = { q[0], q[1], q[2], q[3] };
+        const T dd[3] = { dth[0], dth[1], dth[2] };
+        PhiCoef<T> pp;
+        attitude_step_exact(qq, dd, small_ang_tol, pp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = qq[i];
+        pc = pp;
+    }
 }
 
 // Phi (row-major) from its coefficients

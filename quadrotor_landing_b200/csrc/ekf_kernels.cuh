@@ -186,7 +186,8 @@ template <typename T, bool SYNTH> struct Inputs {
 // tick), so that the 20 sums can be reduced over the warp with shuffles and leave as ONE atomic per warp and
 // statistic instead of one per lane.  Deliberately NOT inlined on the device: it runs once per `stride` ticks
 // and must not take part in the register allocation of the hot loop.
-template <typename T, bool BIAS, class PS>
+// SAVE = false: P is a scratch copy that may be destroyed (the cooperative mapping, ekf_coop.cuh).
+template <typename T, bool BIAS, class PS, bool SAVE = true>
 QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> s, PS P, const double *bias,
                             bool valid)
 {
@@ -219,12 +220,16 @@ QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nom
         }
         // save P, factor in place, restore
         // (the restore is unrolled deep: with 7 warps per SM nothing else hides its DRAM round trips)
+        if (SAVE) {
 #pragma unroll 8
-        for (int el = 0; el < NP; ++el) gp[el * ld] = P.el(el);
+            for (int el = 0; el < NP; ++el) gp[el * ld] = P.el(el);
+        }
         T nees;
         bool ok = nees_inplace<T>(P, e, nees);
+        if (SAVE) {
 #pragma unroll 40
-        for (int el = 0; el < NP; ++el) P.el(el) = gp[el * ld];
+            for (int el = 0; el < NP; ++el) P.el(el) = gp[el * ld];
+        }
         bool finite = true;
 #pragma unroll
         for (int c = 0; c < N; ++c) { finite = finite && (M<T>::abs_(e[c]) < T(1e30)); }

@@ -10,10 +10,12 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "ekf_params.hpp"
 #include "launch.hpp"
+#include "launch_coop.hpp"
 #include "preset.hpp"
 #include "scenario.hpp"
 
@@ -81,6 +83,9 @@ struct qekf_handle {
     size_t d_mask_bytes = 0;
     // launch bookkeeping
     int64_t launches = 0;
+    // mapping of the fused replay (qekf_set_mapping): 3 = cooperative kernel where it exists (FP64, single-rate)
+    int lanes_per_filter = 3;
+    int coop_groups = COOP_GROUPS_DEFAULT;
 };
 
 namespace {
@@ -265,6 +270,19 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
         }
     }
     const bool mr = h->p.multirate_ekf != 0, pf = h->pf_on;
+    if constexpr (std::is_same<T, double>::value) {
+        if (!mr && h->lanes_per_filter == 3) {
+            // three lanes per filter (ekf_coop.cuh)
+            cudaError_t e;
+            if (ns) e = pf ? launch_run_coop<BIAS, DIRECT, true, true>(a, h->coop_groups, h->stream)
+                           : launch_run_coop<BIAS, DIRECT, true, false>(a, h->coop_groups, h->stream);
+            else e = pf ? launch_run_coop<BIAS, DIRECT, false, true>(a, h->coop_groups, h->stream)
+                        : launch_run_coop<BIAS, DIRECT, false, false>(a, h->coop_groups, h->stream);
+            if (e != cudaSuccess) return fail(QEKF_ERR_CUDA, std::string("cooperative replay launch: ") + cudaGetErrorString(e));
+            h->launches++;
+            return QEKF_OK;
+        }
+    }
 #define LAUNCH_(S, MR_, PF_) CUDA_TRY((launch_run<T, BIAS, DIRECT, S, MR_, PF_>(a, grid_of(h), smem_bytes(h), h->stream)))
 #define LAUNCH_S(S)                                                       \
     do {                                                                  \
@@ -456,6 +474,12 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
     qekf_handle *h = new (std::nothrow) qekf_handle;
     if (!h) return fail(QEKF_ERR_ALLOC, "out of host memory");
     h->p = *p; h->precision = precision; h->device = device;
+    {   // environment overrides of the default mapping (profiling / A-B runs): QEKF_LANES=1|3, QEKF_COOP_GROUPS=n
+        const char *e = getenv("QEKF_LANES");
+        if (e && (atoi(e) == 1 || atoi(e) == 3)) h->lanes_per_filter = atoi(e);
+        e = getenv("QEKF_COOP_GROUPS");
+        if (e && coop_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->coop_groups = atoi(e);
+    }
     h->n = n_filters; h->ld = (n_filters + 31) / 32 * 32;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
@@ -557,6 +581,21 @@ int qekf_set_filter_params(qekf_handle *h, int field, const double *values)
 
 int qekf_num_states(const qekf_handle *h) { return h ? h->nstates : 0; }
 int64_t qekf_num_filters(const qekf_handle *h) { return h ? h->n : 0; }
+
+int qekf_set_mapping(qekf_handle *h, int lanes_per_filter, int groups)
+{
+    if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
+    if (lanes_per_filter != 1 && lanes_per_filter != 3) return fail(QEKF_ERR_BAD_ARG, "lanes_per_filter must be 1 or 3");
+    if (groups == 0) groups = COOP_GROUPS_DEFAULT;
+    if (lanes_per_filter == 3) {
+        const bool bench_variant = h->p.est_bias && h->p.direct_orien_method && !h->pf_on;
+        if (!coop_groups_available(groups, bench_variant))
+            return fail(QEKF_ERR_BAD_ARG, "this build has no cooperative kernel with that many groups per CTA for this filter variant");
+        h->coop_groups = groups;
+    }
+    h->lanes_per_filter = lanes_per_filter;
+    return QEKF_OK;
+}
 
 int qekf_set_stream(qekf_handle *h, void *cuda_stream)
 {

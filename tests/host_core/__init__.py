@@ -216,3 +216,87 @@ def count_flops(params):
     out = np.zeros(2)
     lib().hc_count_flops(C.byref(params), _dp(out))
     return int(out[0]), int(out[1])
+
+
+# ---- cooperative (three lanes per filter) code, host-instantiated with race tracing (host_coop.cu) ----
+_COOP_LIB = os.path.join(_HERE, "libhost_coop.so")
+_COOP_SRC = [os.path.join(_HERE, "host_coop.cu")] + [
+    os.path.join(_HERE, "..", "..", "quadrotor_landing_b200", "csrc", f)
+    for f in ("ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_coop.cuh", "ekf_params.hpp")
+]
+_coop = None
+
+
+def build_coop(force=False):
+    if force or not os.path.exists(_COOP_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_COOP_LIB) for s in _COOP_SRC):
+        res = subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
+                              "-fPIC,-pthread", "-shared", "-o", _COOP_LIB, _COOP_SRC[0]],
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("host_coop build failed:\n" + res.stdout)
+    return _COOP_LIB
+
+
+def coop_lib():
+    global _coop
+    if _coop is None:
+        build_coop()
+        _coop = C.CDLL(_COOP_LIB)
+    return _coop
+
+
+def coop_prediction_step(params, x, P, u, order=0):
+    """prediction_step by the three-lane code; lanes run phase by phase in the given order (0..5).
+    Returns x, P, accel and (races seen by the tracer, spread between the lanes' replicas of q/ab/wb)."""
+    n = 15 if params.est_bias else 9
+    x = _f64(x); P = _f64(P); u = _f64(u)
+    xo = np.zeros(16); Po = np.zeros((n, n)); acc = np.zeros(3); diag = np.zeros(2)
+    coop_lib().hcoop_prediction_step(C.byref(params), int(order), _dp(x), _dp(P), _dp(u), _dp(xo), _dp(Po), _dp(acc), _dp(diag))
+    return xo, Po, acc, diag
+
+
+def coop_correction_step(params, x, P, tag, order=0):
+    n = 15 if params.est_bias else 9
+    x = _f64(x); P = _f64(P); tag = _f64(tag)
+    xo = np.zeros(16); Po = np.zeros((n, n)); obs = np.zeros(7); diag = np.zeros(2)
+    coop_lib().hcoop_correction_step(C.byref(params), int(order), _dp(x), _dp(P), _dp(tag), _dp(xo), _dp(Po), _dp(obs), _dp(diag))
+    return xo, Po, obs, diag
+
+
+class CoopHostBatch(HostBatch):
+    """N filters advanced by the product's run_filter_coop() on the host: three threads per filter meeting at a barrier,
+    every shared word traced.  FP64, single-rate.  self.races = races seen by the tracer in the last run."""
+
+    def __init__(self, params, n_filters):
+        assert not params.multirate_ekf
+        super().__init__(params, n_filters, 64)
+        self.races = 0
+
+    def _call(self, k0, n_steps, imu, step, pose, stamp, valid, t_start, noise, truth, stats, stride):
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L = coop_lib()
+        L.hcoop_run.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, C.POINTER(C.c_uint8),
+                                 C.c_double] + [dp] * 4 + [ip] * 2 + [C.c_void_p, dp, dp, C.c_int32, C.c_int32] + [dp] * 6)
+        vptr = valid.ctypes.data_as(C.POINTER(C.c_uint8)) if valid is not None else None
+        pf = [_dp(a) for a in self.pf] if self.pf is not None else [None] * 5
+        diag = np.zeros(2)
+        L.hcoop_run(C.byref(self.p), self.N, int(k0), int(n_steps), _dp(imu), step.shape[0], step.ctypes.data_as(ip),
+                    _dp(pose), _dp(stamp), vptr, float(t_start), _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
+                    self.flags.ctypes.data_as(ip), self.upds.ctypes.data_as(ip),
+                    C.byref(noise) if noise is not None else None, _dp(truth) if truth is not None else None,
+                    _dp(stats) if stats is not None else None, stats.shape[1] if stats is not None else 0, int(stride),
+                    *pf, _dp(diag))
+        self.races = int(diag[0])
+
+    def run(self, k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid=None, t_start=0.0):
+        imu = _f64(imu); tag_pose = _f64(tag_pose); tag_stamp = _f64(tag_stamp)
+        tag_step = np.ascontiguousarray(tag_step, dtype=np.int32)
+        if tag_valid is not None:
+            tag_valid = np.ascontiguousarray(tag_valid, dtype=np.uint8)
+        self._call(k0, n_steps, imu, tag_step, tag_pose, tag_stamp, tag_valid, t_start, None, None, None, 0)
+
+    def run_mc(self, scn, noise, k0=0, n_steps=None, stats=None, stride=0):
+        n_steps = scn.T - k0 if n_steps is None else n_steps
+        imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
+        step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+        self._call(k0, n_steps, imu, step, pose, stamp, None, scn.spec.t_start, noise, truth, stats, stride)

@@ -1,0 +1,400 @@
+// host_coop.cu -- TEST HARNESS (not product): runs the product's cooperative three-lanes-per-filter code
+// (quadrotor_landing_b200/csrc/ekf_coop.cuh) on the HOST, one filter at a time, with the three lanes executed
+// either phase by phase in a chosen order (step-level entry points) or as three threads meeting at a barrier
+// (the full replay loop).  Every shared-word access is traced: two different lanes touching the same word
+// between two barriers, at least one of them writing, is a race and is counted.  On a GPU the same templates
+// run inside run_kernel_coop.
+#define QEKF_COOP_TRACE 1
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <pthread.h>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../quadrotor_landing_b200/csrc/ekf_coop.cuh"
+#include "../../quadrotor_landing_b200/csrc/ekf_params.hpp"
+
+using namespace qekf;
+using namespace qekf::coop;
+
+// ---- race detector -------------------------------------------------------------------------------
+namespace {
+struct WordInfo {
+    int w_lane = -1;
+    long w_epoch = -1;
+    long r_epoch[3] = { -1, -1, -1 };
+    bool written = false;
+};
+std::mutex g_mu;
+std::unordered_map<const void *, WordInfo> g_words;
+long g_epoch = 0;
+long g_races = 0, g_uninit = 0;
+thread_local int t_lane = 0;
+bool g_check_uninit = false;
+const double *g_base = nullptr;   // word 0 of the filter being run (race reports name the word)
+void report(const void *addr, const char *what, int other)
+{
+    if (getenv("QEKF_COOP_TRACE_VERBOSE"))
+        fprintf(stderr, "race %s: word %ld lane %d vs lane %d epoch %ld\n", what, (long)((const double *)addr - g_base), t_lane, other, g_epoch);
+}
+void epoch_next() { std::lock_guard<std::mutex> l(g_mu); ++g_epoch; }
+void trace_reset() { std::lock_guard<std::mutex> l(g_mu); g_words.clear(); g_epoch = 0; g_races = 0; g_uninit = 0; }
+}  // namespace
+
+namespace qekf { namespace coop {
+void coop_trace(const void *addr, int is_write)
+{
+    std::lock_guard<std::mutex> l(g_mu);
+    WordInfo &w = g_words[addr];
+    if (is_write) {
+        if (w.w_epoch == g_epoch && w.w_lane != t_lane) { ++g_races; report(addr, "WAW", w.w_lane); }
+        for (int k = 0; k < 3; ++k)
+            if (k != t_lane && w.r_epoch[k] == g_epoch) { ++g_races; report(addr, "WAR", k); }
+        w.w_lane = t_lane; w.w_epoch = g_epoch; w.written = true;
+    } else {
+        if (w.w_epoch == g_epoch && w.w_lane != t_lane) { ++g_races; report(addr, "RAW", w.w_lane); }
+        if (g_check_uninit && !w.written) ++g_uninit;
+        w.r_epoch[t_lane] = g_epoch;
+    }
+}
+}}
+
+namespace {
+
+template <int NB> void full_to_packed(const double *Pfull, double *pk)
+{
+    constexpr int N = 3 * NB;
+    for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) pk[sym_idx<N>(i, j)] = Pfull[i * N + j];
+}
+template <int NB> void packed_to_full(const double *pk, double *Pfull)
+{
+    constexpr int N = 3 * NB;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) Pfull[i * N + j] = pk[sym_idx<N>(i, j)];
+}
+
+template <int NB> struct Lanes {
+    using PL = PLane<double, NB, 1>;
+    std::vector<double> sh;
+    PL P[3];
+    LaneNominal<double> s[3];
+    Lanes() : sh(Lay<NB>::SLOTS, std::nan("")) {}
+    void load(const double *x, const double *pk)
+    {
+        for (int c = 0; c < 3; ++c) {
+            t_lane = c;
+            P[c].setup(sh.data(), c);
+            cov_load(P[c], pk, 1);
+            for (int a = 0; a < 3; ++a) {
+                s[c].q[a] = x[6 + P[c].gi(a)];
+                s[c].ab[a] = x[10 + P[c].gi(a)];
+                s[c].wb[a] = x[13 + P[c].gi(a)];
+            }
+            s[c].q[3] = x[9];
+            s[c].r0 = x[c]; s[c].v0 = x[3 + c]; s[c].acc0 = 0;
+        }
+        epoch_next();
+    }
+    void store(double *x, double *pk)
+    {
+        for (int c = 0; c < 3; ++c) {
+            t_lane = c;
+            cov_store(P[c], pk, 1);
+            x[c] = s[c].r0; x[3 + c] = s[c].v0;
+        }
+        for (int a = 0; a < 3; ++a) { x[6 + a] = s[0].q[a]; x[10 + a] = s[0].ab[a]; x[13 + a] = s[0].wb[a]; }
+        x[9] = s[0].q[3];
+        epoch_next();
+    }
+    // largest disagreement between the replicas of q / ab / wb held by the three lanes
+    double replica_spread() const
+    {
+        double m = 0;
+        for (int c = 1; c < 3; ++c) {
+            for (int a = 0; a < 3; ++a) {
+                const int g = P[c].gi(a);
+                m = std::fmax(m, std::fabs(s[c].q[a] - s[0].q[g]));
+                m = std::fmax(m, std::fabs(s[c].ab[a] - s[0].ab[g]));
+                m = std::fmax(m, std::fabs(s[c].wb[a] - s[0].wb[g]));
+            }
+            m = std::fmax(m, std::fabs(s[c].q[3] - s[0].q[3]));
+        }
+        return m;
+    }
+};
+
+const int ORDERS[6][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 1, 2, 0 }, { 0, 2, 1 }, { 2, 0, 1 }, { 1, 0, 2 } };
+
+template <bool BIAS> void coop_predict_t(const qekf_params *p, int order, const double *x, const double *Pin, const double *u,
+                                         double *xo, double *Po, double *acc, double *diag)
+{
+    constexpr int NB = BIAS ? 5 : 3, N = 3 * NB;
+    Consts<double> c = make_consts<double>(*p);
+    ParU<double> par{ c };
+    std::vector<double> pk(N * (N + 1) / 2);
+    full_to_packed<NB>(Pin, pk.data());
+    trace_reset();
+    Lanes<NB> L;
+    std::memcpy(xo, x, 16 * sizeof(double));
+    L.load(x, pk.data());
+    TickCarry<double> k[3];
+    const int *o = ORDERS[order % 6];
+    double rcs[3][RC_N];
+    for (int cc = 0; cc < 3; ++cc) fill_role_consts(c, cc, rcs[cc]);
+    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, L.P[cc].c, L.P[cc].i1, L.P[cc].i2, SPtr<double>::from(rcs[cc]) }; };
+    for (int j = 0; j < 3; ++j) {
+        const int cc = o[j];
+        t_lane = cc;
+        double ul[6];
+        for (int a = 0; a < 3; ++a) { ul[a] = u[L.P[cc].gi(a)]; ul[3 + a] = u[3 + L.P[cc].gi(a)]; }
+        auto rp = rp_of(cc);
+        pred_kin(L.s[cc], ul, rp, k[cc]);
+        pred_stage1<BIAS>(L.P[cc], rp, k[cc]);
+    }
+    epoch_next();
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage2<BIAS>(L.P[cc], rp, k[cc]); }
+    epoch_next();
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage3<BIAS>(L.P[cc], rp, k[cc]); }
+    epoch_next();
+    // phase 4 of this tick and phase 1 of the next share a barrier interval: run a second phase 1 on copies of
+    // the lanes' registers to let the detector see that pairing too (its stores are then undone)
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage4<BIAS>(L.P[cc], rp, k[cc]); }
+    {
+        std::vector<double> keep = L.sh;
+        for (int j = 0; j < 3; ++j) {
+            const int cc = o[2 - j];
+            t_lane = cc;
+            auto Pc = L.P[cc];
+            auto kc = k[cc];
+            auto rp = rp_of(cc);
+            pred_stage1<BIAS>(Pc, rp, kc);
+        }
+        {   // the probe's stores are undone without tracing
+            std::lock_guard<std::mutex> l(g_mu);
+            L.sh = keep;
+        }
+    }
+    epoch_next();
+    L.store(xo, pk.data());
+    packed_to_full<NB>(pk.data(), Po);
+    for (int cc = 0; cc < 3; ++cc) acc[cc] = L.s[cc].acc0;
+    diag[0] = (double)g_races;
+    diag[1] = L.replica_spread();
+}
+
+template <bool BIAS, bool DIRECT> void coop_correct_t(const qekf_params *p, int order, const double *x, const double *Pin,
+                                                       const double *tag, double *xo, double *Po, double *obs7, double *diag)
+{
+    constexpr int NB = BIAS ? 5 : 3, N = 3 * NB;
+    Consts<double> c = make_consts<double>(*p);
+    ParU<double> par{ c };
+    std::vector<double> pk(N * (N + 1) / 2);
+    full_to_packed<NB>(Pin, pk.data());
+    trace_reset();
+    Lanes<NB> L;
+    std::memcpy(xo, x, 16 * sizeof(double));
+    L.load(x, pk.data());
+    const int *o = ORDERS[order % 6];
+    CorrCarry<double, NB> cc3[3];
+    Observation<double> obs[3];
+    double rcs[3][RC_N];
+    for (int cc = 0; cc < 3; ++cc) fill_role_consts(c, cc, rcs[cc]);
+    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, L.P[cc].c, L.P[cc].i1, L.P[cc].i2, SPtr<double>::from(rcs[cc]) }; };
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; corr_publish(L.P[cc], L.s[cc]); }
+    epoch_next();
+    for (int j = 0; j < 3; ++j) {
+        const int cc = o[j];
+        t_lane = cc;
+        double tl[7];
+        for (int a = 0; a < 3; ++a) { tl[a] = tag[L.P[cc].gi(a)]; tl[3 + a] = tag[3 + L.P[cc].gi(a)]; }
+        tl[6] = tag[6];
+        auto rp = rp_of(cc);
+        corr_stage1<BIAS, DIRECT>(L.P[cc], L.s[cc], tl, rp, obs[cc], cc3[cc]);
+    }
+    epoch_next();
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; corr_stage2<BIAS>(L.P[cc], L.s[cc], cc3[cc]); }
+    epoch_next();
+    L.store(xo, pk.data());
+    packed_to_full<NB>(pk.data(), Po);
+    for (int cc = 0; cc < 3; ++cc) { obs7[cc] = obs[cc].r_t_vt_obs[0]; obs7[3 + cc] = obs[cc].q_tv_obs[0]; }
+    obs7[6] = obs[0].q_tv_obs[3];
+    diag[0] = (double)g_races;
+    diag[1] = L.replica_spread();
+}
+
+// ---- the full replay loop: three threads per filter meeting at a barrier ---------------------------
+struct Bar3 {
+    pthread_barrier_t b;
+    Bar3() { pthread_barrier_init(&b, nullptr, 3); }
+    ~Bar3() { pthread_barrier_destroy(&b); }
+    static void wait(void *ctx)
+    {
+        Bar3 *self = static_cast<Bar3 *>(ctx);
+        if (pthread_barrier_wait(&self->b) == PTHREAD_BARRIER_SERIAL_THREAD) epoch_next();
+        pthread_barrier_wait(&self->b);
+    }
+};
+
+struct McArgs {
+    const NoiseSpec *ns;
+    const double *truth;
+    double *stats_acc;
+    int32_t n_bins, stride;
+};
+
+template <bool BIAS, bool DIRECT>
+void coop_run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
+                const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
+                double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+                const McArgs *mc, const double *const *pf, double *diag)
+{
+    constexpr int NB = BIAS ? 5 : 3, NS = 3 * NB, NP = NS * (NS + 1) / 2;
+    RunArgs<double> a;
+    std::memset(&a, 0, sizeof a);
+    a.st.x = x; a.st.P = Ppk; a.st.aux = aux; a.st.pend = pend;
+    a.st.flags = flags; a.st.upds = upds; a.st.counts = nullptr; a.st.ld = N; a.st.n = N;
+    a.in.imu = imu; a.in.tag_step = tag_step; a.in.tag_pose = tag_pose; a.in.tag_stamp = tag_stamp;
+    a.in.tag_valid = tag_valid; a.in.cs = N; a.in.is = 1; a.in.M = M; a.in.vs = N;
+    a.in.t_start = t_start; a.in.update_freq = p->update_freq;
+    a.c = make_consts<double>(*p);
+    a.k0 = k0; a.n_steps = n_steps;
+    int32_t m0 = 0;
+    while (m0 < M && tag_step[m0] < k0) ++m0;
+    a.m0 = m0;
+    std::vector<uint8_t> mask;
+    std::vector<double> sig;
+    const bool synth = mc && mc->ns;
+    if (synth) {
+        a.in.cs = 1; a.in.is = 0; a.in.vs = 0; a.in.tag_valid = nullptr;
+        a.ns = *mc->ns;
+        if (a.ns.edge_loss) {
+            mask.resize((size_t)M);
+            visibility_mask(tag_pose, M, make_consts<double>(*p), mask.data());
+            a.in.tag_valid = mask.data();
+        }
+        if (a.ns.range_ref > 0) {
+            sig.resize((size_t)M * 2);
+            range_sigmas(tag_pose, M, a.ns, sig.data());
+            a.in.tag_sigma = sig.data();
+        }
+        if (mc->stats_acc && mc->truth) {
+            a.stats.acc = mc->stats_acc; a.stats.truth = mc->truth; a.stats.n_bins = mc->n_bins; a.stats.stride = mc->stride;
+            a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
+            a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
+        }
+    }
+    std::vector<double> pft, pfd;
+    if (pf && pf[0]) {
+        pft.assign((size_t)PF_DIM * N, 0.0);
+        pfd.assign(2 * (size_t)N, 0.0);
+        qekf_params q = *p;
+        for (int64_t i = 0; i < N; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                q.Q_a[k] = pf[0][(0 + k) * N + i]; q.Q_w[k] = pf[0][(3 + k) * N + i];
+                q.Q_ab[k] = pf[0][(6 + k) * N + i]; q.Q_wb[k] = pf[0][(9 + k) * N + i];
+                q.R_r[k] = pf[1][(0 + k) * N + i]; q.R_ang[k] = pf[1][(3 + k) * N + i];
+                q.r_v_cv[k] = pf[2][k * N + i];
+            }
+            for (int k = 0; k < 4; ++k) q.q_vc[k] = pf[3][k * N + i];
+            fill_pf_column<double>(q, pft.data() + i, N);
+            pfd[i] = pf[4][i]; pfd[N + i] = pf[4][N + i];
+        }
+        a.st.pf = pft.data(); a.st.pf_delay = pfd.data();
+    }
+    double rcs[3][RC_N];
+    for (int cc = 0; cc < 3; ++cc) fill_role_consts(a.c, cc, rcs[cc]);
+    trace_reset();
+    double spread = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        std::vector<double> sh(Lay<NB>::SLOTS, std::nan(""));
+        std::vector<double> scratch(NP + 6, 0.0);
+        Bar3 bar;
+        g_base = sh.data();
+        auto lane_main = [&](int cc) {
+            t_lane = cc;
+            PLane<double, NB, 1> P;
+            P.setup(sh.data(), cc);
+            GroupSync gs{ 0, &Bar3::wait, &bar };
+            CtaCtx<double> cta{ 0, 1, scratch.data() };
+            if (a.st.pf) {
+                const ParF<double> par = ParSel<double, true>::make(a.c, a.st, i);
+                const RotPar<double, ParF<double>> rp{ par, a.c, P.c, P.i1, P.i2, SPtr<double>::from(rcs[cc]) };
+                if (synth) run_filter_coop<double, BIAS, DIRECT, true>(a, i, P, rp, true, gs, cta);
+                else run_filter_coop<double, BIAS, DIRECT, false>(a, i, P, rp, true, gs, cta);
+            } else {
+                const ParU<double> par{ a.c };
+                const RotPar<double, ParU<double>> rp{ par, a.c, P.c, P.i1, P.i2, SPtr<double>::from(rcs[cc]) };
+                if (synth) run_filter_coop<double, BIAS, DIRECT, true>(a, i, P, rp, true, gs, cta);
+                else run_filter_coop<double, BIAS, DIRECT, false>(a, i, P, rp, true, gs, cta);
+            }
+        };
+        std::thread t1(lane_main, 1), t2(lane_main, 2);
+        lane_main(0);
+        t1.join(); t2.join();
+        {   // drop this filter's words from the tracer (the vector is about to be freed and its addresses reused)
+            std::lock_guard<std::mutex> l(g_mu);
+            g_words.clear();
+        }
+    }
+    diag[0] = (double)g_races;
+    diag[1] = spread;
+}
+
+}  // namespace
+
+extern "C" {
+
+// state arrays as hc_run (x [16][N], Ppk [NP][N] packed, aux [11][N], pend [8][N], flags [N], upds [N]); FP64, single-rate.
+// ns == NULL: explicit streams.  pf_*: per-filter overrides or all NULL.
+void hcoop_run(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
+               const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
+               double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+               const qekf_noise_spec *n, const double *truth, double *stats_acc, int32_t n_bins, int32_t stride,
+               const double *pf_q, const double *pf_r, const double *pf_rvcv, const double *pf_qvc, const double *pf_delay,
+               double *diag)
+{
+    NoiseSpec ns;
+    McArgs mc = { nullptr, truth, stats_acc, n_bins, stride };
+    if (n) {
+        std::memset(&ns, 0, sizeof ns);
+        ns.seed = n->seed; ns.gid0 = n->first_global_id;
+        ns.sig_a = (float)n->sigma_accel; ns.sig_w = (float)n->sigma_gyro;
+        ns.sig_ba = (float)n->sigma_bias_accel; ns.sig_bw = (float)n->sigma_bias_gyro;
+        ns.sig_p = (float)n->sigma_tag_pos; ns.sig_th = (float)n->sigma_tag_ang;
+        ns.drop_k0 = n->dropout_k0; ns.drop_k1 = n->dropout_k1;
+        ns.rdrop_len = n->rand_dropout_len; ns.rdrop_lo = n->rand_dropout_lo; ns.rdrop_hi = n->rand_dropout_hi;
+        ns.edge_loss = n->edge_loss; ns.range_ref = n->range_ref; ns.range_exp_p = n->range_exp_pos; ns.range_exp_th = n->range_exp_ang;
+        mc.ns = &ns;
+    }
+    const double *pf[5] = { pf_q, pf_r, pf_rvcv, pf_qvc, pf_delay };
+    const bool b = p->est_bias != 0, d = p->direct_orien_method != 0;
+#define C_(B, D) coop_run_t<B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds, &mc, pf, diag)
+    if (b && d) C_(true, true); else if (b) C_(true, false); else if (d) C_(false, true); else C_(false, false);
+#undef C_
+}
+
+void hcoop_prediction_step(const qekf_params *p, int order, const double *x, const double *P, const double *u, double *xo,
+                           double *Po, double *acc, double *diag)
+{
+    if (p->est_bias) coop_predict_t<true>(p, order, x, P, u, xo, Po, acc, diag);
+    else coop_predict_t<false>(p, order, x, P, u, xo, Po, acc, diag);
+}
+
+void hcoop_correction_step(const qekf_params *p, int order, const double *x, const double *P, const double *tag, double *xo,
+                           double *Po, double *obs7, double *diag)
+{
+    const bool b = p->est_bias != 0, d = p->direct_orien_method != 0;
+    if (b && d) coop_correct_t<true, true>(p, order, x, P, tag, xo, Po, obs7, diag);
+    else if (b) coop_correct_t<true, false>(p, order, x, P, tag, xo, Po, obs7, diag);
+    else if (d) coop_correct_t<false, true>(p, order, x, P, tag, xo, Po, obs7, diag);
+    else coop_correct_t<false, false>(p, order, x, P, tag, xo, Po, obs7, diag);
+}
+
+}  // extern "C"
