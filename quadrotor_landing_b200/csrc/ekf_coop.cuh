@@ -22,6 +22,16 @@
 // in row c).  Those 15 values live in the lane's registers; shared memory holds the other 75 (600 B per filter)
 // and every column access costs two shared-memory words instead of three.
 //
+// Roles.  The nominal state is not replicated: role 0 (lane c = 0, whose local frame is the global one) holds it,
+// runs the nominal kinematics of a tick and publishes the Jacobian pieces (B = -dT C, the specific force a, dT w and
+// the coefficients of Phi) through a double-buffered exchange; meanwhile roles 1 and 2 draw the next tick's noisy
+// IMU sample (Philox + Box-Muller), so neither job is replicated and neither serialises the other.  Roles are
+// whole warps, so the split costs no divergence.
+//
+// Addressing.  Word (a,b), a != b, of a 3x3 block lives at slot ((a-b) mod 3 - 1)*3 + b, word {a,b} of a symmetric
+// diagonal block at slot 3-a-b.  With that numbering every access of lane c is one of three base pointers
+// (word c, word (c+1)%3, word (c+2)%3 of the filter) plus a compile-time offset.
+//
 // Nothing here is a port of the reference: what is computed is prediction_step / correction_step
 // (relative_pose_EKF.cpp:346-502); how it is computed is specific to this mapping.
 #pragma once
@@ -34,8 +44,9 @@ namespace coop {
 // ------------------------------------------------------------------------------------------------
 // storage layout of one filter's shared words (units of T; word e of filter f lives at base[e*S + f])
 // ------------------------------------------------------------------------------------------------
-QEKF_FN constexpr int l6(int a, int b) { return 2 * a + (b > a ? b - 1 : b); }   // off-diagonal entry (a,b), a != b, of a 3x3
-QEKF_FN constexpr int l3(int a, int b) { return a + b - 1; }                     // entry {a,b}, a != b, of a symmetric 3x3
+QEKF_FN constexpr int odslot(int a, int b) { return ((a - b + 3) % 3 - 1) * 3 + b; }   // entry (a,b), a != b, of a 3x3 block
+QEKF_FN constexpr int dgslot(int a, int b) { return 3 - a - b; }                        // entry {a,b}, a != b, of a symmetric 3x3
+QEKF_FN constexpr int fullslot(int a, int b) { return ((a - b + 3) % 3) * 3 + b; }      // entry (a,b) of a full 3x3 (9 words)
 
 template <int NB> QEKF_FN constexpr int bidx(int X, int Y) { return X * NB - (X * (X - 1)) / 2 + (Y - X); }   // X <= Y
 template <int NB> QEKF_FN constexpr int sbase(int X, int Y)   // X <= Y: first shared word of block (X,Y)
@@ -60,16 +71,17 @@ template <int NB> QEKF_FN constexpr int pubidx(int X, int Y)
 template <int NB> struct Lay {
     static constexpr int NPRIV = NB * (NB + 1) / 2;          // 15 / 6 private (register) entries per lane
     static constexpr int NSH = 3 * NB + 3 * NB * (NB - 1);   // 75 / 27 shared covariance words
-    static constexpr int UB = NSH;                           // noisy IMU sample of the next tick, 6 words (global order)
-    static constexpr int XV = NSH + 6;                       // exchange of the (v,v) row update, 6 words (off-diagonal of a 3x3)
-    static constexpr int XT = NSH + 12;                      // exchange of Phi*P(th,th)
-    static constexpr int CB = NSH + 18;                      // ---- words used by corrections / statistics only ----
+    static constexpr int UB = NSH;                           // noisy IMU samples [2 ticks][6], global order
+    static constexpr int JB = UB + 12;                       // kinematics exchange [2 ticks][JB_N]
+    static constexpr int JB_B = 0, JB_A = 9, JB_DTH = 12, JB_PC = 15, JB_N = 18;   // B (fullslot), a, dT w, (cs, s1, s2)
+    static constexpr int XV = JB + 2 * JB_N;                 // exchange of the (v,v) row update, 6 words (odslot)
+    static constexpr int XT = XV + 6;                        // exchange of Phi*P(th,th)
+    static constexpr int CB = XT + 6;                        // ---- words used by corrections / statistics only ----
     static constexpr int NPUB = (NB == 5) ? 9 : 5;
     static constexpr int PB = CB;                            // published private entries [NPUB][3 lanes]
     static constexpr int DX = PB + 3 * NPUB;                 // injected error state [NB][3 lanes]
-    static constexpr int RB = DX + 3 * NB;                   // r [3 lanes]
-    static constexpr int VB = RB + 3;                        // v [3 lanes]
-    static constexpr int SLOTS = VB + 3;                     // 141 / 72
+    static constexpr int QR = DX + 3 * NB;                   // nominal attitude (vector part [3], w) and position [3], global order
+    static constexpr int SLOTS = QR + 7;                     // 190 / 121
 };
 
 // Shared-memory words are addressed through SPtr: on the device a 32-bit shared-window address used by explicit
@@ -121,24 +133,19 @@ template <typename T, int NB_, int S_> struct PLane {
     using L = Lay<NB_>;
     T priv[L::NPRIV];             // entry (c,c) of every block, X <= Y at bidx(X,Y)
     SPtr<T> sh;                   // word 0 of this filter
-    SPtr<T> p1, p2;               // + sbase*S: entries (i1,c), (i2,c) of an off-diagonal block   (column c)
-    SPtr<T> q1, q2;               //            entries (c,i1), (c,i2)                            (row c)
-    SPtr<T> d1, d2;               //            entries {i1,c}, {i2,c} of a diagonal block
-    SPtr<T> pc, pa, pb;           // + w*S: word w+c, w+i1, w+i2 of a [..][3 lanes] exchange array
-    int c, i1, i2;
+    SPtr<T> pc, pa, pb;           // words c, i1 = (c+1)%3, i2 = (c+2)%3 of this filter
+    int c;
     bool wc1, wc2, wr1, wr2;      // who stores a diagonal block's shared entries: column form (i < c), row form (i > c)
 
     QEKF_FN void setup(T *filter_base, int c_)
     {
-        c = c_; i1 = (c_ + 1) % 3; i2 = (c_ + 2) % 3;
+        c = c_;
+        const int i1 = (c_ + 1) % 3, i2 = (c_ + 2) % 3;
         sh = SPtr<T>::from(filter_base);
-        p1 = sh + l6(i1, c) * S_; p2 = sh + l6(i2, c) * S_;
-        q1 = sh + l6(c, i1) * S_; q2 = sh + l6(c, i2) * S_;
-        d1 = sh + l3(i1, c) * S_; d2 = sh + l3(i2, c) * S_;
         pc = sh + c * S_; pa = sh + i1 * S_; pb = sh + i2 * S_;
         wc1 = i1 < c; wc2 = i2 < c; wr1 = i1 > c; wr2 = i2 > c;
     }
-    QEKF_FN int gi(int a) const { return a == 0 ? c : (a == 1 ? i1 : i2); }   // local -> global component
+    QEKF_FN int gi(int a) const { return (c + a) % 3; }   // local -> global component (cold paths only)
 };
 
 // column c of block (X,Y), i.e. P[3X + (a+c)%3, 3Y + c] for local a = 0,1,2 -- whatever the storage orientation
@@ -147,13 +154,13 @@ template <int X, int Y, class PL> QEKF_FN void col_ld(const PL &P, typename PL::
     constexpr int NB = PL::nb, S = PL::stride;
     if constexpr (X < Y) {
         constexpr int b = sbase<NB>(X, Y) * S;
-        v[0] = P.priv[bidx<NB>(X, Y)]; v[1] = sm_ld(P.p1 + b); v[2] = sm_ld(P.p2 + b);
+        v[0] = P.priv[bidx<NB>(X, Y)]; v[1] = sm_ld(P.pc + b); v[2] = sm_ld(P.pc + (b + 3 * S));
     } else if constexpr (X > Y) {
         constexpr int b = sbase<NB>(Y, X) * S;
-        v[0] = P.priv[bidx<NB>(Y, X)]; v[1] = sm_ld(P.q1 + b); v[2] = sm_ld(P.q2 + b);
+        v[0] = P.priv[bidx<NB>(Y, X)]; v[1] = sm_ld(P.pa + (b + 3 * S)); v[2] = sm_ld(P.pb + b);
     } else {
         constexpr int b = sbase<NB>(X, X) * S;
-        v[0] = P.priv[bidx<NB>(X, X)]; v[1] = sm_ld(P.d1 + b); v[2] = sm_ld(P.d2 + b);
+        v[0] = P.priv[bidx<NB>(X, X)]; v[1] = sm_ld(P.pb + b); v[2] = sm_ld(P.pa + b);
     }
 }
 // store column c of block (X,Y); of a diagonal block only the upper entries (i < c) -- the others belong to
@@ -163,15 +170,15 @@ template <int X, int Y, class PL> QEKF_FN void col_st(PL &P, const typename PL::
     constexpr int NB = PL::nb, S = PL::stride;
     if constexpr (X < Y) {
         constexpr int b = sbase<NB>(X, Y) * S;
-        P.priv[bidx<NB>(X, Y)] = v[0]; sm_st(P.p1 + b, v[1]); sm_st(P.p2 + b, v[2]);
+        P.priv[bidx<NB>(X, Y)] = v[0]; sm_st(P.pc + b, v[1]); sm_st(P.pc + (b + 3 * S), v[2]);
     } else if constexpr (X > Y) {
         constexpr int b = sbase<NB>(Y, X) * S;
-        P.priv[bidx<NB>(Y, X)] = v[0]; sm_st(P.q1 + b, v[1]); sm_st(P.q2 + b, v[2]);
+        P.priv[bidx<NB>(Y, X)] = v[0]; sm_st(P.pa + (b + 3 * S), v[1]); sm_st(P.pb + b, v[2]);
     } else {
         constexpr int b = sbase<NB>(X, X) * S;
         P.priv[bidx<NB>(X, X)] = v[0];
-        if (P.wc1) sm_st(P.d1 + b, v[1]);
-        if (P.wc2) sm_st(P.d2 + b, v[2]);
+        if (P.wc1) sm_st(P.pb + b, v[1]);
+        if (P.wc2) sm_st(P.pa + b, v[2]);
     }
 }
 // store ROW c of diagonal block (X,X): v[k] = P[3X + c, 3X + (k+c)%3]; upper entries (i > c) only
@@ -180,8 +187,8 @@ template <int X, class PL> QEKF_FN void row_st(PL &P, const typename PL::real v[
     constexpr int NB = PL::nb, S = PL::stride;
     constexpr int b = sbase<NB>(X, X) * S;
     P.priv[bidx<NB>(X, X)] = v[0];
-    if (P.wr1) sm_st(P.d1 + b, v[1]);
-    if (P.wr2) sm_st(P.d2 + b, v[2]);
+    if (P.wr1) sm_st(P.pb + b, v[1]);
+    if (P.wr2) sm_st(P.pa + b, v[2]);
 }
 // a whole block (X <= Y) of the dr / dth block columns in local indices, b[a*3+k] = P[3X+gi(a), 3Y+gi(k)]; the
 // private entries of the other two lanes come from the published copies (corr_publish)
@@ -196,15 +203,32 @@ template <int X, int Y, class PL> QEKF_FN void full_ld(const PL &P, typename PL:
     b[4] = sm_ld(P.pa + pw);
     b[8] = sm_ld(P.pb + pw);
     if constexpr (X < Y) {
-        b[3] = sm_ld(P.p1 + sb); b[6] = sm_ld(P.p2 + sb);
-        b[1] = sm_ld(P.q1 + sb); b[2] = sm_ld(P.q2 + sb);
-        b[5] = sm_ld(P.sh + l6(P.i1, P.i2) * S + sb);
-        b[7] = sm_ld(P.sh + l6(P.i2, P.i1) * S + sb);
+        b[3] = sm_ld(P.pc + sb); b[6] = sm_ld(P.pc + (sb + 3 * S));
+        b[1] = sm_ld(P.pa + (sb + 3 * S)); b[2] = sm_ld(P.pb + sb);
+        b[5] = sm_ld(P.pb + (sb + 3 * S));
+        b[7] = sm_ld(P.pa + sb);
     } else {
-        b[1] = b[3] = sm_ld(P.d1 + sb);
-        b[2] = b[6] = sm_ld(P.d2 + sb);
-        b[5] = b[7] = sm_ld(P.sh + l3(P.i1, P.i2) * S + sb);
+        b[1] = b[3] = sm_ld(P.pb + sb);
+        b[2] = b[6] = sm_ld(P.pa + sb);
+        b[5] = b[7] = sm_ld(P.pc + sb);
     }
+}
+// a 3-vector / the rows of a full 3x3 published in GLOBAL order, read in local order
+template <class PL> QEKF_FN void vec_ld(const PL &P, int w, typename PL::real v[3])
+{
+    constexpr int S = PL::stride;
+    v[0] = sm_ld(P.pc + w * S); v[1] = sm_ld(P.pa + w * S); v[2] = sm_ld(P.pb + w * S);
+}
+template <class PL> QEKF_FN void mat_ld(const PL &P, int w, typename PL::real m[9])   // published at fullslot(a,b)
+{
+    constexpr int S = PL::stride;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int d = ((a - k + 3) % 3) * 3;
+            m[a * 3 + k] = sm_ld((k == 0 ? P.pc : (k == 1 ? P.pa : P.pb)) + (w + d) * S);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,8 +239,8 @@ template <int NB> QEKF_FN constexpr int packed_of_word(int X, int Y, int w)
 {
     constexpr int N = 3 * NB;
     int a = 0, b = 0;
-    if (X == Y) { a = (w == 2) ? 1 : 0; b = (w == 0) ? 1 : 2; }
-    else { a = w / 2; const int r = w % 2; b = (r >= a) ? r + 1 : r; }
+    if (X == Y) { a = (w == 0) ? 1 : 0; b = (w == 2) ? 1 : 2; }          // slot = the index that is missing
+    else { b = w % 3; a = (b + w / 3 + 1) % 3; }                          // slot = ((a-b) mod 3 - 1)*3 + b
     return sym_idx<N>(3 * X + a, 3 * Y + b);
 }
 // Each lane moves the shared words w with w % 3 == c of every block, and its own private entries.
@@ -347,19 +371,9 @@ template <typename T> QEKF_FN void rot3(const T g[3], int c, T l[3])
     l[2] = c == 0 ? g[2] : (c == 1 ? g[0] : g[1]);
 }
 
-// nominal state of the filter as one lane holds it (local indices)
-template <typename T> struct LaneNominal {
-    T q[4];           // vector part relabelled, then w
-    T ab[3], wb[3];
-    T r0, v0;         // component c of r and v (the other two live in the other lanes)
-    T acc0;           // component c of accel_rel
-};
-
 // what a tick carries from one phase to the next
 template <typename T> struct TickCarry {
-    T B[9], a[3];     // B = -dT C (row-major), a = specific force; A = B skew(a) is applied as B (a x .)
-    T dth[3];
-    PhiCoef<T> pc;
+    T B[9], a[3];     // B = -dT C (row-major), a = specific force, in local indices; A = B skew(a) is applied as B (a x .)
     T accR[3], accT[3];
     T Mv0, PD0;
 };
@@ -383,37 +397,86 @@ template <typename T> QEKF_FN void mv_acc(const T A[9], const T t[3], T o[3])   
 }
 
 // ------------------------------------------------------------------------------------------------
-// prediction_step, phase 0: nominal kinematics and the Jacobian pieces (replicated in the three lanes; each
-// lane keeps its own component of r, v, accel_rel)                         relative_pose_EKF.cpp:346-401
+// prediction_step, phase 0 (role 0 only): nominal kinematics, and the Jacobian pieces published for all three
+// lanes at word offset `jw` (this tick's half of the exchange)               relative_pose_EKF.cpp:346-401
 // ------------------------------------------------------------------------------------------------
-template <typename T, class RP> QEKF_FN void pred_kin(LaneNominal<T> &s, const T u[6], const RP &rp, TickCarry<T> &k)
+template <typename T, class PL>
+QEKF_FN void kin_step(Nominal<T> &s, T accel[3], const T u[6], const Consts<T> &c, PL &P, int jw)
 {
-    const T d = rp.c.dT;
-    T w[3], C[9];
+    constexpr int S = PL::stride;
+    using L = typename PL::L;
+    const T d = c.dT;
+    T a[3], w[3], C[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        k.a[i] = u[i] - s.ab[i] - rp.ab_static(i);
-        w[i] = u[3 + i] - s.wb[i] - rp.wb_static(i);
+        a[i] = u[i] - s.ab[i] - c.ab_static[i];
+        w[i] = u[3 + i] - s.wb[i] - c.wb_static[i];
     }
     quat_to_rot(s.q, C);
-    const T acc = M<T>::fma_(C[2], k.a[2], M<T>::fma_(C[1], k.a[1], C[0] * k.a[0])) + rp.g(0);
-    s.acc0 = acc;
-    s.r0 = M<T>::fma_(d, s.v0, s.r0);     // uses the old v (explicit Euler)
-    s.v0 = M<T>::fma_(d, acc, s.v0);
+    T acc[3];
+    mv(C, a, acc);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) k.B[i] = -d * C[i];
+    for (int i = 0; i < 3; ++i) {
+        acc[i] += c.g[i];
+        accel[i] = acc[i];
+        s.r[i] = M<T>::fma_(d, s.v[i], s.r[i]);     // uses the old v (explicit Euler)
+    }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) k.dth[i] = d * w[i];
-    attitude_step(s.q, k.dth, rp.c.small_ang_tol, k.pc);
+    for (int i = 0; i < 3; ++i) s.v[i] = M<T>::fma_(d, acc[i], s.v[i]);
+    const SPtr<T> j = P.sh + jw * S;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sm_st(j + (L::JB_B + fullslot(r, k)) * S, -d * C[r * 3 + k]);
+    T dth[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dth[i] = d * w[i];
+        sm_st(j + (L::JB_A + i) * S, a[i]);
+        sm_st(j + (L::JB_DTH + i) * S, dth[i]);
+    }
+    PhiCoef<T> pc;
+    attitude_step(s.q, dth, c.small_ang_tol, pc);
+    sm_st(j + (L::JB_PC + 0) * S, pc.cs);
+    sm_st(j + (L::JB_PC + 1) * S, pc.s1);
+    sm_st(j + (L::JB_PC + 2) * S, pc.s2);
+}
+
+// this lane's base pointers shifted by a run-time word offset (one half of a double-buffered exchange)
+template <typename T> struct Tri { SPtr<T> c, a, b, h; };
+template <class PL> QEKF_FN Tri<typename PL::real> tri(const PL &P, int w)
+{
+    constexpr int S = PL::stride;
+    return Tri<typename PL::real>{ P.pc + w * S, P.pa + w * S, P.pb + w * S, P.sh + w * S };
+}
+// Phi (row-major, local indices) from the published dT w and coefficients
+template <class PL, typename T = typename PL::real> QEKF_FN void phi_ld(const PL &P, int jw, T Phi[9])
+{
+    constexpr int S = PL::stride;
+    using L = typename PL::L;
+    const Tri<T> j = tri(P, jw);
+    const T dth[3] = { sm_ld(j.c + L::JB_DTH * S), sm_ld(j.a + L::JB_DTH * S), sm_ld(j.b + L::JB_DTH * S) };
+    const PhiCoef<T> pc{ sm_ld(j.h + (L::JB_PC + 0) * S), sm_ld(j.h + (L::JB_PC + 1) * S), sm_ld(j.h + (L::JB_PC + 2) * S) };
+    phi_matrix(pc, dth, Phi);
 }
 
 // Phase 1: E1 on the columns (r,Y) += dT (v,Y); the parts of the (r,r) and (v,v) updates that need OLD values.
 template <bool BIAS, class PL, class RP, typename T = typename PL::real>
-QEKF_FN void pred_stage1(PL &P, const RP &rp, TickCarry<T> &k)
+QEKF_FN void pred_stage1(PL &P, const RP &rp, TickCarry<T> &k, int jw)
 {
     constexpr int S = PL::stride;
     using L = typename PL::L;
     const T d = rp.c.dT;
+    {   // B and a of this tick, relabelled: entry (r,k) of B sits at fullslot(r,k) = ((r-k) mod 3)*3 + k
+        const Tri<T> j = tri(P, jw);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            k.B[r * 3 + 0] = sm_ld(j.c + (L::JB_B + ((r + 3) % 3) * 3) * S);
+            k.B[r * 3 + 1] = sm_ld(j.a + (L::JB_B + ((r + 2) % 3) * 3) * S);
+            k.B[r * 3 + 2] = sm_ld(j.b + (L::JB_B + ((r + 1) % 3) * 3) * S);
+        }
+        k.a[0] = sm_ld(j.c + L::JB_A * S); k.a[1] = sm_ld(j.a + L::JB_A * S); k.a[2] = sm_ld(j.b + L::JB_A * S);
+    }
     T vv[3], x[3], y[3], t[3];
     col_ld<BV, BV>(P, vv);
     col_ld<BR, BV>(P, x);
@@ -451,8 +514,8 @@ QEKF_FN void pred_stage1(PL &P, const RP &rp, TickCarry<T> &k)
     }
     mv_acc(k.B, t, vv);
     k.Mv0 = vv[0];
-    sm_st(P.p1 + L::XV * S, vv[1]);
-    sm_st(P.p2 + L::XV * S, vv[2]);
+    sm_st(P.pc + L::XV * S, vv[1]);
+    sm_st(P.pc + (L::XV + 3) * S, vv[2]);
 }
 
 // Phase 2: finish (r,r); E2 on the columns (v,Y) += A (th,Y) + B (ab,Y), Y != v.
@@ -492,7 +555,7 @@ QEKF_FN void pred_stage2(PL &P, const RP &rp, TickCarry<T> &k)
 
 // Phase 3: finish (v,v) (row c, + C Qa C^T); E3 on the columns (th,Y) <- Phi (th,Y) - dT (wb,Y), Y != th.
 template <bool BIAS, class PL, class RP, typename T = typename PL::real>
-QEKF_FN void pred_stage3(PL &P, const RP &rp, TickCarry<T> &k)
+QEKF_FN void pred_stage3(PL &P, const RP &rp, TickCarry<T> &k, int jw)
 {
     constexpr int S = PL::stride;
     using L = typename PL::L;
@@ -501,8 +564,8 @@ QEKF_FN void pred_stage3(PL &P, const RP &rp, TickCarry<T> &k)
     col_ld<BTH, BV>(P, nt);               // row c of the new (v,th)
     if constexpr (BIAS) { col_ld<BAB, BV>(P, y); cross_add(k.a, nt, y, t); } else { cross_set(k.a, nt, t); }
     vr[0] = k.Mv0;
-    vr[1] = sm_ld(P.q1 + L::XV * S);
-    vr[2] = sm_ld(P.q2 + L::XV * S);
+    vr[1] = sm_ld(P.pa + (L::XV + 3) * S);
+    vr[2] = sm_ld(P.pb + L::XV * S);
     mv_acc(k.B, t, vr);
     {   // + row c of C diag(Qa) C^T = (B diag(Qa) B^T) / dT^2
         const T inv = T(1) / (d * d);
@@ -513,7 +576,7 @@ QEKF_FN void pred_stage3(PL &P, const RP &rp, TickCarry<T> &k)
     }
     row_st<BV>(P, vr);
     T Phi[9];
-    phi_matrix(k.pc, k.dth, Phi);
+    phi_ld(P, jw, Phi);
     // (th,r)
     col_ld<BTH, BR>(P, x);
     if constexpr (BIAS) {
@@ -560,20 +623,20 @@ QEKF_FN void pred_stage3(PL &P, const RP &rp, TickCarry<T> &k)
     for (int i = 0; i < 3; ++i) t[i] = T(0);
     mv_acc(Phi, x, t);
     k.PD0 = t[0];
-    sm_st(P.p1 + L::XT * S, t[1]);
-    sm_st(P.p2 + L::XT * S, t[2]);
+    sm_st(P.pc + L::XT * S, t[1]);
+    sm_st(P.pc + (L::XT + 3) * S, t[2]);
 }
 
 // Phase 4: finish (th,th) (row c), process noise on the diagonals.
 template <bool BIAS, class PL, class RP, typename T = typename PL::real>
-QEKF_FN void pred_stage4(PL &P, const RP &rp, TickCarry<T> &k)
+QEKF_FN void pred_stage4(PL &P, const RP &rp, TickCarry<T> &k, int jw)
 {
     constexpr int S = PL::stride, NB = PL::nb;
     using L = typename PL::L;
     const T d = rp.c.dT;
-    T pd[3] = { k.PD0, sm_ld(P.q1 + L::XT * S), sm_ld(P.q2 + L::XT * S) };
+    T pd[3] = { k.PD0, sm_ld(P.pa + (L::XT + 3) * S), sm_ld(P.pb + L::XT * S) };
     T Phi[9], tr[3];
-    phi_matrix(k.pc, k.dth, Phi);
+    phi_ld(P, jw, Phi);
     if constexpr (BIAS) {
         T nw[3];
         col_ld<BWB, BTH>(P, nw);          // row c of the new (th,wb)
@@ -608,8 +671,9 @@ template <typename T, int NB> struct CorrCarry {
     T dx[NB];                  // component c of the injected error of every block
 };
 
+// `s`: the nominal state (role 0) or nullptr (roles 1, 2)
 template <class PL, typename T = typename PL::real>
-QEKF_FN void corr_publish(PL &P, const LaneNominal<T> &s)
+QEKF_FN void corr_publish(PL &P, const Nominal<T> *s)
 {
     constexpr int S = PL::stride, NB = PL::nb;
     using L = typename PL::L;
@@ -618,7 +682,12 @@ QEKF_FN void corr_publish(PL &P, const LaneNominal<T> &s)
 #pragma unroll
         for (int Y = X; Y < NB; ++Y)
             if (pubidx<NB>(X, Y) >= 0) sm_st(P.pc + (L::PB + 3 * pubidx<NB>(X, Y)) * S, P.priv[bidx<NB>(X, Y)]);
-    sm_st(P.pc + L::RB * S, s.r0);
+    if (s) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sm_st(P.sh + (L::QR + i) * S, s->q[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sm_st(P.sh + (L::QR + 4 + i) * S, s->r[i]);
+    }
 }
 
 // gain row, injected error and the new dr / dth entries of this lane's column of block Y
@@ -699,8 +768,8 @@ template <int X, int Y, class PL, typename T> QEKF_FN void corr_down(PL &P, cons
     if constexpr (X == Y) {
         constexpr int b = sbase<PL::nb>(X, X) * PL::stride;
         v[0] = P.priv[bidx<PL::nb>(X, X)];
-        v[1] = P.wc1 ? sm_ld(P.d1 + b) : T(0);
-        v[2] = P.wc2 ? sm_ld(P.d2 + b) : T(0);
+        v[1] = P.wc1 ? sm_ld(P.pb + b) : T(0);
+        v[2] = P.wc2 ? sm_ld(P.pa + b) : T(0);
     } else {
         col_ld<X, Y>(P, v);
     }
@@ -716,15 +785,17 @@ template <int X, int Y, class PL, typename T> QEKF_FN void corr_down(PL &P, cons
 
 // Phase B.  `tag` is the tag pose in local indices, `obs` comes back in local indices.
 template <bool BIAS, bool DIRECT, class PL, class RP, typename T = typename PL::real>
-QEKF_FN void corr_stage1(PL &P, const LaneNominal<T> &s, const T tag[7], const RP &rp, Observation<T> &obs,
-                         CorrCarry<T, PL::nb> &cc)
+QEKF_FN void corr_stage1(PL &P, const T tag[7], const RP &rp, Observation<T> &obs, CorrCarry<T, PL::nb> &cc)
 {
     constexpr int S = PL::stride;
     using L = typename PL::L;
     T dy[6], Rk[21], Gam[9], Sinv[21];
-    {
-        const T r[3] = { s.r0, sm_ld(P.pa + L::RB * S), sm_ld(P.pb + L::RB * S) };
-        correction_front<T, DIRECT>(s.q, r, tag, rp, obs, dy, Rk, Gam);
+    {   // the published nominal attitude and position, relabelled
+        T q[4], r[3];
+        vec_ld(P, L::QR, q);
+        q[3] = sm_ld(P.sh + (L::QR + 3) * S);
+        vec_ld(P, L::QR + 4, r);
+        correction_front<T, DIRECT>(q, r, tag, rp, obs, dy, Rk, Gam);
     }
     {   // S = G P G^T + R_k, inverted through Cholesky (as the thread-per-filter path)
         T rr[9], rt[9], tt[9], Brt[36], Sm[21];
@@ -797,12 +868,10 @@ QEKF_FN void corr_stage1(PL &P, const LaneNominal<T> &s, const T tag[7], const R
     }
 }
 
-// Phase C.
+// Phase C: the new dr / dth columns.
 template <bool BIAS, class PL, typename T = typename PL::real>
-QEKF_FN void corr_stage2(PL &P, LaneNominal<T> &s, const CorrCarry<T, PL::nb> &cc)
+QEKF_FN void corr_stage2(PL &P, const CorrCarry<T, PL::nb> &cc)
 {
-    constexpr int S = PL::stride;
-    using L = typename PL::L;
     col_st<BR, BR>(P, cc.nr[BR]);
     col_st<BR, BV>(P, cc.nr[BV]);
     col_st<BTH, BV>(P, cc.nt[BV]);
@@ -814,10 +883,20 @@ QEKF_FN void corr_stage2(PL &P, LaneNominal<T> &s, const CorrCarry<T, PL::nb> &c
         col_st<BR, BWB>(P, cc.nr[BWB]);
         col_st<BTH, BWB>(P, cc.nt[BWB]);
     }
-    // injection (cpp:484-498)
-    s.r0 += cc.dx[BR];
-    s.v0 += cc.dx[BV];
-    const T dth[3] = { cc.dx[BTH], sm_ld(P.pa + (L::DX + 3 * BTH) * S), sm_ld(P.pb + (L::DX + 3 * BTH) * S) };
+}
+// ... and (role 0) the injection of the error state into the nominal one (cpp:484-498)
+template <bool BIAS, class PL, typename T = typename PL::real>
+QEKF_FN void corr_inject(const PL &P, Nominal<T> &s)
+{
+    constexpr int S = PL::stride;
+    using L = typename PL::L;
+    T dth[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        s.r[i] += sm_ld(P.sh + (L::DX + 3 * BR + i) * S);
+        s.v[i] += sm_ld(P.sh + (L::DX + 3 * BV + i) * S);
+        dth[i] = sm_ld(P.sh + (L::DX + 3 * BTH + i) * S);
+    }
     {
         T qe[4], qn[4], nn, sh, ch;
         quat_exp(dth, qe, nn, sh, ch);
@@ -826,16 +905,14 @@ QEKF_FN void corr_stage2(PL &P, LaneNominal<T> &s, const CorrCarry<T, PL::nb> &c
 #pragma unroll
         for (int i = 0; i < 4; ++i) s.q[i] = qn[i];
     }
-    if constexpr (BIAS) {
-        s.ab[0] += cc.dx[BAB];
-        s.ab[1] += sm_ld(P.pa + (L::DX + 3 * BAB) * S);
-        s.ab[2] += sm_ld(P.pb + (L::DX + 3 * BAB) * S);
-        s.wb[0] += cc.dx[BWB];
-        s.wb[1] += sm_ld(P.pa + (L::DX + 3 * BWB) * S);
-        s.wb[2] += sm_ld(P.pb + (L::DX + 3 * BWB) * S);
-    } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { s.ab[i] = T(0); s.wb[i] = T(0); }
+    for (int i = 0; i < 3; ++i) {
+        if constexpr (BIAS) {
+            s.ab[i] += sm_ld(P.sh + (L::DX + 3 * BAB + i) * S);
+            s.wb[i] += sm_ld(P.sh + (L::DX + 3 * BWB + i) * S);
+        } else {
+            s.ab[i] = T(0); s.wb[i] = T(0);
+        }
     }
 }
 
@@ -901,29 +978,41 @@ template <typename T, int N> struct PNull {
     QEKF_FN void st(int, int, T) {}
 };
 
-// this lane's two components (2c, 2c+1) of the noisy IMU sample of tick k -- the same realisation synth_imu
-// draws: one Philox call and one Box-Muller pair per lane instead of two and three per filter
-QEKF_FN void synth_imu_pair(const NoiseSpec &ns, int64_t gid, int64_t k, int c, const double *clean6, const double bias2[2],
-                            double out[2])
+// Roles 1 and 2 draw the noisy IMU sample of tick k -- the realisation synth_imu draws -- into half `uw` of the
+// exchange: role 1 components 0..3 (first Philox call, two Box-Muller pairs), role 2 components 4, 5 (second call).
+template <class PL, typename T = typename PL::real>
+QEKF_FN void synth_imu_role(const NoiseSpec &ns, int64_t gid, int64_t k, const double *clean6, const double bias[4], PL &P, int uw)
 {
+    constexpr int S = PL::stride;
     uint32_t w[4];
     const uint32_t k0 = (uint32_t)ns.seed, k1 = (uint32_t)(ns.seed >> 32);
     const uint32_t g0 = (uint32_t)(uint64_t)gid, g1 = (uint32_t)((uint64_t)gid >> 32);
-    philox4x32_10((uint32_t)k, STREAM_IMU + (c == 2 ? 1u : 0u), g0, g1, k0, k1, w);
-    float z0, z1;
-    box_muller(c == 1 ? w[2] : w[0], c == 1 ? w[3] : w[1], z0, z1);
-    const double s0 = (double)(c <= 1 ? ns.sig_a : ns.sig_w), s1 = (double)(c == 0 ? ns.sig_a : ns.sig_w);
-    out[0] = clean6[2 * c] + bias2[0] + s0 * (double)z0;
-    out[1] = clean6[2 * c + 1] + bias2[1] + s1 * (double)z1;
+    const SPtr<T> u = P.sh + uw * S;
+    if (P.c == 1) {
+        philox4x32_10((uint32_t)k, STREAM_IMU, g0, g1, k0, k1, w);
+        float z0, z1, z2, z3;
+        box_muller(w[0], w[1], z0, z1);
+        box_muller(w[2], w[3], z2, z3);
+        sm_st(u + 0 * S, (T)(clean6[0] + bias[0] + (double)ns.sig_a * (double)z0));
+        sm_st(u + 1 * S, (T)(clean6[1] + bias[1] + (double)ns.sig_a * (double)z1));
+        sm_st(u + 2 * S, (T)(clean6[2] + bias[2] + (double)ns.sig_a * (double)z2));
+        sm_st(u + 3 * S, (T)(clean6[3] + bias[3] + (double)ns.sig_w * (double)z3));
+    } else {
+        philox4x32_10((uint32_t)k, STREAM_IMU + 1u, g0, g1, k0, k1, w);
+        float z4, z5;
+        box_muller(w[0], w[1], z4, z5);
+        sm_st(u + 4 * S, (T)(clean6[4] + bias[0] + (double)ns.sig_w * (double)z4));
+        sm_st(u + 5 * S, (T)(clean6[5] + bias[1] + (double)ns.sig_w * (double)z5));
+    }
 }
 
-// One statistics sample of the group's 32 filters: the three lanes assemble the packed covariance and the
-// nominal state in the scratch, lane 0's warp runs the thread-per-filter sampling code on that copy.
+// One statistics sample of the group's 32 filters: the three lanes assemble the packed covariance in the scratch,
+// role 0 (which holds the nominal state) runs the thread-per-filter sampling code on that copy.
 template <typename T, bool BIAS, class PL>
-QEKF_COLD void coop_stats_sample(const RunArgs<T> &a, int64_t i, int64_t k_done, const PL P, const LaneNominal<T> s,
-                                 T *scr, bool mine, const GroupSync gs)
+QEKF_COLD void coop_stats_sample(const RunArgs<T> &a, int64_t i, int64_t k_done, const PL P, const Nominal<T> s, T *scr,
+                                 bool mine, const GroupSync gs)
 {
-    constexpr int NB = PL::nb, N = 3 * NB, NP = N * (N + 1) / 2, S = PL::stride;
+    constexpr int NB = PL::nb, N = 3 * NB, S = PL::stride;
 #ifdef __CUDA_ARCH__
     const SPtr<T> my = SPtr<T>::from(scr + (threadIdx.x & 31));
     constexpr int SS = 32;
@@ -940,21 +1029,11 @@ QEKF_COLD void coop_stats_sample(const RunArgs<T> &a, int64_t i, int64_t k_done,
             for (int w = 0; w < (X == Y ? 3 : 6); ++w)
                 if ((w % 3) == P.c) sm_st(my + packed_of_word<NB>(X, Y, w) * SS, sm_ld(P.sh + (sbase<NB>(X, Y) + w) * S));
         }
-    sm_st(my + (NP + P.c) * SS, s.r0);
-    sm_st(my + (NP + 3 + P.c) * SS, s.v0);
     gs.sync();
     if (P.c == 0) {
-        Nominal<T> n;
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            n.r[cc] = sm_ld(my + (NP + cc) * SS);
-            n.v[cc] = sm_ld(my + (NP + 3 + cc) * SS);
-            n.q[cc] = s.q[cc]; n.ab[cc] = s.ab[cc]; n.wb[cc] = s.wb[cc];
-        }
-        n.q[3] = s.q[3];
         double bias[6];
         true_bias(a.ns, a.ns.gid0 + i, bias);
-        stats_sample<T, BIAS, PShared<T, N, SS>, false>(a, i, k_done, n, PShared<T, N, SS>{ my.generic() }, bias, mine);
+        stats_sample<T, BIAS, PShared<T, N, SS>, false>(a, i, k_done, s, PShared<T, N, SS>{ my.generic() }, bias, mine);
     }
 }
 
@@ -971,44 +1050,38 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
     const int64_t k_end = a.k0 + a.n_steps;
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
-    const bool lead = P.c == 0;            // the lane that stores what all three hold
+    const bool lead = P.c == 0;            // role 0: holds the nominal state, does the kinematics, stores the scalars
 
-    LaneNominal<T> s;
+    Nominal<T> s;                          // role 0 only
+    T accel[3] = { T(0), T(0), T(0) };     // role 0 only
+    double nb[4] = { 0, 0, 0, 0 };         // roles 1, 2: the true bias of the components they draw
     int32_t flags = 0, upds = 0;
     Inputs<T, SYNTH> in;
-    double bias2[2] = { 0, 0 };
     int64_t k = k_end;
-    s.acc0 = T(0); s.r0 = T(0); s.v0 = T(0);
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc) { s.q[cc] = T(0); s.ab[cc] = T(0); s.wb[cc] = T(0); }
+    for (int cc = 0; cc < 3; ++cc) { s.r[cc] = T(0); s.v[cc] = T(0); s.q[cc] = T(0); s.ab[cc] = T(0); s.wb[cc] = T(0); }
     s.q[3] = T(1);
     if (live) {
-        const T *x = a.st.x + i;
         const int64_t ld = a.st.ld;
-        s.r0 = x[(0 + P.c) * ld];
-        s.v0 = x[(3 + P.c) * ld];
+        if (lead) {
+            const T *x = a.st.x + i;
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            s.q[cc] = x[(6 + P.gi(cc)) * ld];
-            s.ab[cc] = x[(10 + P.gi(cc)) * ld];
-            s.wb[cc] = x[(13 + P.gi(cc)) * ld];
+            for (int cc = 0; cc < 3; ++cc) {
+                s.r[cc] = x[(0 + cc) * ld]; s.v[cc] = x[(3 + cc) * ld]; s.q[cc] = x[(6 + cc) * ld];
+                s.ab[cc] = x[(10 + cc) * ld]; s.wb[cc] = x[(13 + cc) * ld];
+                accel[cc] = a.st.aux[cc * ld + i];
+            }
+            s.q[3] = x[9 * ld];
         }
-        s.q[3] = x[9 * ld];
-        s.acc0 = a.st.aux[P.c * ld + i];
         cov_load(P, a.st.P + i, ld);
         flags = a.st.flags[i];
         upds = a.st.upds[i];
         in.init(a, i);
         k = a.k0;
-        if (SYNTH) {
-            bias2[0] = P.c == 0 ? in.bias[0] : (P.c == 1 ? in.bias[2] : in.bias[4]);
-            bias2[1] = P.c == 0 ? in.bias[1] : (P.c == 1 ? in.bias[3] : in.bias[5]);
-            if (k < k_end) {
-                double u2[2];
-                synth_imu_pair(a.ns, in.gid, k, P.c, a.in.imu + k * 6, bias2, u2);
-                sm_st(P.sh + (L::UB + 2 * P.c) * S, (T)u2[0]);
-                sm_st(P.sh + (L::UB + 2 * P.c + 1) * S, (T)u2[1]);
-            }
+        if (SYNTH && !lead) {
+            if (P.c == 1) { nb[0] = in.bias[0]; nb[1] = in.bias[1]; nb[2] = in.bias[2]; nb[3] = in.bias[3]; }
+            else { nb[0] = in.bias[4]; nb[1] = in.bias[5]; }
+            if (k < k_end) synth_imu_role(a.ns, in.gid, k, a.in.imu + k * 6, nb, P, L::UB + 6 * (int)(k & 1));
         }
     }
     gs.sync();
@@ -1032,19 +1105,12 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
-                    T tg[7], tl[7];
-                    in.tag(a.in, m, tg);
-                    rot3(tg, P.c, tl);
-                    rot3(tg + 3, P.c, tl + 3);
-                    tl[6] = tg[6];
-                    Nominal<T> n;
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) { n.ab[cc] = s.ab[cc]; n.wb[cc] = s.wb[cc]; }
-                    PNull<T, 3 * NB> pn;
-                    initialize_state<T, BIAS>(n, pn, tl, rp, false);
-                    s.r0 = n.r[0]; s.v0 = T(0);
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) s.q[cc] = n.q[cc];
+                    if (lead) {        // initialize_state (cpp:305-344): the nominal part, in role 0's (= the global) frame
+                        T tg[7];
+                        in.tag(a.in, m, tg);
+                        PNull<T, 3 * NB> pn;
+                        initialize_state<T, BIAS>(s, pn, tg, rp, false);   // role 0's parameter view is not relabelled
+                    }
                     cov_init(P, c);
                     flags |= FLAG_INIT;
                     init_now = true;
@@ -1101,54 +1167,53 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
         }
 
         if (v.active != 0) {
-            // ---- prediction (cpp:240-249) in four phases ----
-            TickCarry<T> tc;
-            if (exec) {
-                T u[6];
-                if (SYNTH) {
+            const int par = (int)(k & 1);
+            const int jw = L::JB + L::JB_N * par;
+            // ---- phase 0: role 0 runs the nominal kinematics of tick k, roles 1 and 2 draw the sample of tick k+1 ----
+            if (lead) {
+                if (exec) {
+                    T u[6];
+                    if (SYNTH) {
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        u[cc] = sm_ld(P.sh + (L::UB + P.gi(cc)) * S);
-                        u[3 + cc] = sm_ld(P.sh + (L::UB + 3 + P.gi(cc)) * S);
-                    }
-                } else {
+                        for (int cc = 0; cc < 6; ++cc) u[cc] = sm_ld(P.sh + (L::UB + 6 * par + cc) * S);
+                    } else {
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        u[cc] = (T)in.imu_i[(k * 6 + P.gi(cc)) * in.cs];
-                        u[3 + cc] = (T)in.imu_i[(k * 6 + 3 + P.gi(cc)) * in.cs];
+                        for (int cc = 0; cc < 6; ++cc) u[cc] = (T)in.imu_i[(k * 6 + cc) * in.cs];
                     }
+                    kin_step(s, accel, u, c, P, jw);
+                    ++n_pred;
                 }
-                pred_kin(s, u, rp, tc);
-                pred_stage1<BIAS>(P, rp, tc);
+            } else if (SYNTH) {
+                if (adv && k + 1 < k_end) synth_imu_role(a.ns, in.gid, k + 1, a.in.imu + (k + 1) * 6, nb, P, L::UB + 6 * (1 - par));
             }
+            gs.sync();
+            // ---- prediction (cpp:402-414) in four phases ----
+            TickCarry<T> tc;
+            if (exec) pred_stage1<BIAS>(P, rp, tc, jw);
             gs.sync();
             if (exec) pred_stage2<BIAS>(P, rp, tc);
-            if (SYNTH && adv && k + 1 < k_end) {     // the next tick's sample (everybody has read this tick's)
-                double u2[2];
-                synth_imu_pair(a.ns, in.gid, k + 1, P.c, a.in.imu + (k + 1) * 6, bias2, u2);
-                sm_st(P.sh + (L::UB + 2 * P.c) * S, (T)u2[0]);
-                sm_st(P.sh + (L::UB + 2 * P.c + 1) * S, (T)u2[1]);
-            }
             gs.sync();
-            if (exec) pred_stage3<BIAS>(P, rp, tc);
+            if (exec) pred_stage3<BIAS>(P, rp, tc, jw);
             gs.sync();
-            if (exec) {
-                pred_stage4<BIAS>(P, rp, tc);
-                if (lead) ++n_pred;
-            }
+            if (exec) pred_stage4<BIAS>(P, rp, tc, jw);
             // ---- single-rate correction (cpp:265-279) ----
             if (group_any(perform)) {
                 CorrCarry<T, NB> cc;
                 Observation<T> obs;
-                if (perform) corr_publish(P, s);
+                if (perform) corr_publish(P, lead ? &s : nullptr);
                 gs.sync();
-                if (perform) corr_stage1<BIAS, DIRECT>(P, s, tag, rp, obs, cc);
+                if (perform) corr_stage1<BIAS, DIRECT>(P, tag, rp, obs, cc);
                 gs.sync();
                 if (perform) {
-                    corr_stage2<BIAS>(P, s, cc);
-                    a.st.aux[(3 + P.c) * a.st.ld + i] = obs.r_t_vt_obs[0];
-                    a.st.aux[(6 + P.c) * a.st.ld + i] = obs.q_tv_obs[0];
-                    if (lead) { a.st.aux[9 * a.st.ld + i] = obs.q_tv_obs[3]; ++n_corr; }
+                    corr_stage2<BIAS>(P, cc);
+                    if (lead) {
+                        corr_inject<BIAS>(P, s);
+#pragma unroll
+                        for (int q3 = 0; q3 < 3; ++q3) a.st.aux[(3 + q3) * a.st.ld + i] = obs.r_t_vt_obs[q3];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) a.st.aux[(6 + q4) * a.st.ld + i] = obs.q_tv_obs[q4];
+                        ++n_corr;
+                    }
                 }
                 gs.sync();
             }
@@ -1179,14 +1244,15 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
     }
     {
-        T *x = a.st.x + i;
         const int64_t ld = a.st.ld;
-        x[(0 + P.c) * ld] = s.r0;
-        x[(3 + P.c) * ld] = s.v0;
-        a.st.aux[P.c * ld + i] = s.acc0;
         if (lead) {
+            T *x = a.st.x + i;
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) { x[(6 + cc) * ld] = s.q[cc]; x[(10 + cc) * ld] = s.ab[cc]; x[(13 + cc) * ld] = s.wb[cc]; }
+            for (int cc = 0; cc < 3; ++cc) {
+                x[(0 + cc) * ld] = s.r[cc]; x[(3 + cc) * ld] = s.v[cc]; x[(6 + cc) * ld] = s.q[cc];
+                x[(10 + cc) * ld] = s.ab[cc]; x[(13 + cc) * ld] = s.wb[cc];
+                a.st.aux[cc * ld + i] = accel[cc];
+            }
             x[9 * ld] = s.q[3];
             a.st.flags[i] = flags;
             a.st.upds[i] = upds;
@@ -1231,7 +1297,7 @@ __global__ void __launch_bounds__(96 * G, 1) run_kernel_coop(const __grid_consta
     const SPtr<T> rc = SPtr<T>::from(rcs + c * RC_N);
     if constexpr (PF) {
         const ParF<T> par = ParSel<T, true>::make(a.c, a.st, live ? i : 0);
-        const RotPar<T, ParF<T>> rp{ par, a.c, P.c, P.i1, P.i2, rc };
+        const RotPar<T, ParF<T>> rp{ par, a.c, P.c, (P.c + 1) % 3, (P.c + 2) % 3, rc };
         run_filter_coop<T, BIAS, DIRECT, SYNTH>(a, i, P, rp, live, gs, cta);
     } else {
         const ParS<T> rp{ a.c, rc };

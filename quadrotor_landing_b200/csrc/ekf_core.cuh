@@ -443,12 +443,16 @@ QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const PAR &p
 // (A = -dT C skew(a), B = -dT C, Phi = F_theta_theta), so  F P F^T  is three in-place symmetric
 // congruences, each touching one block row/column.  W Q W^T = blockdiag(0, C Qa C^T, Qw, Qab, Qwb).
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool BIAS, class PS, class PAR>
-QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par, T accel[3])
+// Jacobian pieces of one tick: A = -dT C skew(a), B = -dT C, Phi = F_theta_theta, QV = C diag(Q_a) C^T (upper)
+template <typename T> struct PredJac { T A[9], B[9], Phi[9], QV[6]; };
+
+// the nominal half of prediction_step (cpp:346-401): kinematics, and the Jacobian pieces from the pre-update state
+template <typename T, class PAR>
+QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3], PredJac<T> &J)
 {
     const Consts<T> &c = par.c;
     const T d = c.dT;
-    T A[9], B[9], Phi[9], QV[6];
+    T *A = J.A, *B = J.B, *Phi = J.Phi, *QV = J.QV;
     {
         T a[3], w[3], C[9];
 #pragma unroll
@@ -494,7 +498,14 @@ QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par,
         attitude_step(s.q, dth, c.small_ang_tol, pc);
         phi_matrix(pc, dth, Phi);
     }
+}
 
+// the covariance half (cpp:402-414): P <- F P F^T + W Q W^T through the three in-place congruences
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_FN void pred_cov(PS &P, const PredJac<T> &J, const PAR &par)
+{
+    const T d = par.c.dT;
+    const T *A = J.A, *B = J.B, *Phi = J.Phi, *QV = J.QV;
     // ---- E1: dr += dT dv -------------------------------------------------------------------
     {
         T vv[9], rv[9], rvn[9];
@@ -647,6 +658,14 @@ QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par,
             }
         }
     }
+}
+
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_FN void prediction_step(Nominal<T> &s, PS &P, const T u[6], const PAR &par, T accel[3])
+{
+    PredJac<T> J;
+    pred_nominal(s, u, par, accel, J);
+    pred_cov<T, BIAS>(P, J, par);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -84,7 +84,8 @@ template <int NB> struct Lanes {
     using PL = PLane<double, NB, 1>;
     std::vector<double> sh;
     PL P[3];
-    LaneNominal<double> s[3];
+    Nominal<double> s;        // role 0's
+    double accel[3];
     Lanes() : sh(Lay<NB>::SLOTS, std::nan("")) {}
     void load(const double *x, const double *pk)
     {
@@ -92,14 +93,9 @@ template <int NB> struct Lanes {
             t_lane = c;
             P[c].setup(sh.data(), c);
             cov_load(P[c], pk, 1);
-            for (int a = 0; a < 3; ++a) {
-                s[c].q[a] = x[6 + P[c].gi(a)];
-                s[c].ab[a] = x[10 + P[c].gi(a)];
-                s[c].wb[a] = x[13 + P[c].gi(a)];
-            }
-            s[c].q[3] = x[9];
-            s[c].r0 = x[c]; s[c].v0 = x[3 + c]; s[c].acc0 = 0;
         }
+        for (int a = 0; a < 3; ++a) { s.r[a] = x[a]; s.v[a] = x[3 + a]; s.q[a] = x[6 + a]; s.ab[a] = x[10 + a]; s.wb[a] = x[13 + a]; accel[a] = 0; }
+        s.q[3] = x[9];
         epoch_next();
     }
     void store(double *x, double *pk)
@@ -107,26 +103,10 @@ template <int NB> struct Lanes {
         for (int c = 0; c < 3; ++c) {
             t_lane = c;
             cov_store(P[c], pk, 1);
-            x[c] = s[c].r0; x[3 + c] = s[c].v0;
         }
-        for (int a = 0; a < 3; ++a) { x[6 + a] = s[0].q[a]; x[10 + a] = s[0].ab[a]; x[13 + a] = s[0].wb[a]; }
-        x[9] = s[0].q[3];
+        for (int a = 0; a < 3; ++a) { x[a] = s.r[a]; x[3 + a] = s.v[a]; x[6 + a] = s.q[a]; x[10 + a] = s.ab[a]; x[13 + a] = s.wb[a]; }
+        x[9] = s.q[3];
         epoch_next();
-    }
-    // largest disagreement between the replicas of q / ab / wb held by the three lanes
-    double replica_spread() const
-    {
-        double m = 0;
-        for (int c = 1; c < 3; ++c) {
-            for (int a = 0; a < 3; ++a) {
-                const int g = P[c].gi(a);
-                m = std::fmax(m, std::fabs(s[c].q[a] - s[0].q[g]));
-                m = std::fmax(m, std::fabs(s[c].ab[a] - s[0].ab[g]));
-                m = std::fmax(m, std::fabs(s[c].wb[a] - s[0].wb[g]));
-            }
-            m = std::fmax(m, std::fabs(s[c].q[3] - s[0].q[3]));
-        }
-        return m;
     }
 };
 
@@ -148,45 +128,32 @@ template <bool BIAS> void coop_predict_t(const qekf_params *p, int order, const 
     const int *o = ORDERS[order % 6];
     double rcs[3][RC_N];
     for (int cc = 0; cc < 3; ++cc) fill_role_consts(c, cc, rcs[cc]);
-    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, L.P[cc].c, L.P[cc].i1, L.P[cc].i2, SPtr<double>::from(rcs[cc]) }; };
-    for (int j = 0; j < 3; ++j) {
-        const int cc = o[j];
-        t_lane = cc;
-        double ul[6];
-        for (int a = 0; a < 3; ++a) { ul[a] = u[L.P[cc].gi(a)]; ul[3 + a] = u[3 + L.P[cc].gi(a)]; }
-        auto rp = rp_of(cc);
-        pred_kin(L.s[cc], ul, rp, k[cc]);
-        pred_stage1<BIAS>(L.P[cc], rp, k[cc]);
-    }
+    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, cc, (cc + 1) % 3, (cc + 2) % 3, SPtr<double>::from(rcs[cc]) }; };
+    const int jw = Lay<NB>::JB + Lay<NB>::JB_N;      // the odd half of the kinematics exchange
+    t_lane = 0;
+    kin_step(L.s, L.accel, u, c, L.P[0], jw);
+    epoch_next();
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage1<BIAS>(L.P[cc], rp, k[cc], jw); }
     epoch_next();
     for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage2<BIAS>(L.P[cc], rp, k[cc]); }
     epoch_next();
-    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage3<BIAS>(L.P[cc], rp, k[cc]); }
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage3<BIAS>(L.P[cc], rp, k[cc], jw); }
     epoch_next();
-    // phase 4 of this tick and phase 1 of the next share a barrier interval: run a second phase 1 on copies of
-    // the lanes' registers to let the detector see that pairing too (its stores are then undone)
-    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage4<BIAS>(L.P[cc], rp, k[cc]); }
+    // phase 4 of this tick shares a barrier interval with phase 0 of the next (role 0 writing the other half of the
+    // exchange, roles 1-2 the next sample): run that pairing on copies to let the detector see it
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; auto rp = rp_of(cc); pred_stage4<BIAS>(L.P[cc], rp, k[cc], jw); }
     {
-        std::vector<double> keep = L.sh;
-        for (int j = 0; j < 3; ++j) {
-            const int cc = o[2 - j];
-            t_lane = cc;
-            auto Pc = L.P[cc];
-            auto kc = k[cc];
-            auto rp = rp_of(cc);
-            pred_stage1<BIAS>(Pc, rp, kc);
-        }
-        {   // the probe's stores are undone without tracing
-            std::lock_guard<std::mutex> l(g_mu);
-            L.sh = keep;
-        }
+        t_lane = 0;
+        Nominal<double> s2 = L.s;
+        double a2[3];
+        kin_step(s2, a2, u, c, L.P[0], Lay<NB>::JB);
     }
     epoch_next();
     L.store(xo, pk.data());
     packed_to_full<NB>(pk.data(), Po);
-    for (int cc = 0; cc < 3; ++cc) acc[cc] = L.s[cc].acc0;
+    for (int cc = 0; cc < 3; ++cc) acc[cc] = L.accel[cc];
     diag[0] = (double)g_races;
-    diag[1] = L.replica_spread();
+    diag[1] = 0;
 }
 
 template <bool BIAS, bool DIRECT> void coop_correct_t(const qekf_params *p, int order, const double *x, const double *Pin,
@@ -206,8 +173,8 @@ template <bool BIAS, bool DIRECT> void coop_correct_t(const qekf_params *p, int 
     Observation<double> obs[3];
     double rcs[3][RC_N];
     for (int cc = 0; cc < 3; ++cc) fill_role_consts(c, cc, rcs[cc]);
-    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, L.P[cc].c, L.P[cc].i1, L.P[cc].i2, SPtr<double>::from(rcs[cc]) }; };
-    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; corr_publish(L.P[cc], L.s[cc]); }
+    auto rp_of = [&](int cc) { return RotPar<double, ParU<double>>{ par, c, cc, (cc + 1) % 3, (cc + 2) % 3, SPtr<double>::from(rcs[cc]) }; };
+    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; corr_publish(L.P[cc], cc == 0 ? &L.s : nullptr); }
     epoch_next();
     for (int j = 0; j < 3; ++j) {
         const int cc = o[j];
@@ -216,17 +183,29 @@ template <bool BIAS, bool DIRECT> void coop_correct_t(const qekf_params *p, int 
         for (int a = 0; a < 3; ++a) { tl[a] = tag[L.P[cc].gi(a)]; tl[3 + a] = tag[3 + L.P[cc].gi(a)]; }
         tl[6] = tag[6];
         auto rp = rp_of(cc);
-        corr_stage1<BIAS, DIRECT>(L.P[cc], L.s[cc], tl, rp, obs[cc], cc3[cc]);
+        corr_stage1<BIAS, DIRECT>(L.P[cc], tl, rp, obs[cc], cc3[cc]);
     }
     epoch_next();
-    for (int j = 0; j < 3; ++j) { const int cc = o[j]; t_lane = cc; corr_stage2<BIAS>(L.P[cc], L.s[cc], cc3[cc]); }
+    for (int j = 0; j < 3; ++j) {
+        const int cc = o[j];
+        t_lane = cc;
+        corr_stage2<BIAS>(L.P[cc], cc3[cc]);
+        if (cc == 0) corr_inject<BIAS>(L.P[0], L.s);
+    }
     epoch_next();
     L.store(xo, pk.data());
     packed_to_full<NB>(pk.data(), Po);
-    for (int cc = 0; cc < 3; ++cc) { obs7[cc] = obs[cc].r_t_vt_obs[0]; obs7[3 + cc] = obs[cc].q_tv_obs[0]; }
+    for (int cc = 0; cc < 3; ++cc) { obs7[cc] = obs[0].r_t_vt_obs[cc]; obs7[3 + cc] = obs[0].q_tv_obs[cc]; }
     obs7[6] = obs[0].q_tv_obs[3];
+    // the three lanes computed the observation in their own relabelling: they must agree
+    double spread = 0;
+    for (int cc = 1; cc < 3; ++cc)
+        for (int a = 0; a < 3; ++a) {
+            spread = std::fmax(spread, std::fabs(obs[cc].r_t_vt_obs[a] - obs[0].r_t_vt_obs[L.P[cc].gi(a)]));
+            spread = std::fmax(spread, std::fabs(obs[cc].q_tv_obs[a] - obs[0].q_tv_obs[L.P[cc].gi(a)]));
+        }
     diag[0] = (double)g_races;
-    diag[1] = L.replica_spread();
+    diag[1] = spread;
 }
 
 // ---- the full replay loop: three threads per filter meeting at a barrier ---------------------------
@@ -325,12 +304,12 @@ void coop_run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, co
             CtaCtx<double> cta{ 0, 1, scratch.data() };
             if (a.st.pf) {
                 const ParF<double> par = ParSel<double, true>::make(a.c, a.st, i);
-                const RotPar<double, ParF<double>> rp{ par, a.c, P.c, P.i1, P.i2, SPtr<double>::from(rcs[cc]) };
+                const RotPar<double, ParF<double>> rp{ par, a.c, cc, (cc + 1) % 3, (cc + 2) % 3, SPtr<double>::from(rcs[cc]) };
                 if (synth) run_filter_coop<double, BIAS, DIRECT, true>(a, i, P, rp, true, gs, cta);
                 else run_filter_coop<double, BIAS, DIRECT, false>(a, i, P, rp, true, gs, cta);
             } else {
                 const ParU<double> par{ a.c };
-                const RotPar<double, ParU<double>> rp{ par, a.c, P.c, P.i1, P.i2, SPtr<double>::from(rcs[cc]) };
+                const RotPar<double, ParU<double>> rp{ par, a.c, cc, (cc + 1) % 3, (cc + 2) % 3, SPtr<double>::from(rcs[cc]) };
                 if (synth) run_filter_coop<double, BIAS, DIRECT, true>(a, i, P, rp, true, gs, cta);
                 else run_filter_coop<double, BIAS, DIRECT, false>(a, i, P, rp, true, gs, cta);
             }
