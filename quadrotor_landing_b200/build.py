@@ -21,7 +21,7 @@ REPLAY_SRC = [os.path.join(ROOT, "tools", "replay_driver.cpp"), os.path.join(ROO
               os.path.join(ROOT, "include", "qekf.h")]
 HEADERS = ["ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp", "scenario.hpp", "preset.hpp", "launch.hpp",
            "launch_coop.hpp", os.path.join("..", "..", "include", "qekf.h")]
-COOP_HEADERS = ["ekf_coop.cuh"]
+COOP_HEADERS = ["ekf_coop.cuh", "ekf_duo.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -29,8 +29,9 @@ def _units():
     units = [("qekf_capi", "qekf_capi.cu", []), ("inst_misc", "inst_misc.cu", [])]
     # the cooperative kernel's units first: the benchmark variant (b1 d1 s1) is the longest compile
     for b, d, sy in ((1, 1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, 1, 1), (0, 1, 0), (0, 0, 1), (0, 0, 0)):
-        units.append(("inst_coop_b%d_d%d_s%d" % (b, d, sy), "inst_coop.cu",
-                      ["-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d, "-DQ_SYNTH=%d" % sy]))
+        for kind in ("duo", "coop"):
+            units.append(("inst_%s_b%d_d%d_s%d" % (kind, b, d, sy), "inst_%s.cu" % kind,
+                          ["-DQ_BIAS=%d" % b, "-DQ_DIRECT=%d" % d, "-DQ_SYNTH=%d" % sy]))
     for t in ("double", "float"):
         for b in (1, 0):
             for d in (1, 0):
@@ -44,12 +45,12 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = HEADERS + COOP_HEADERS + ["qekf_capi.cu", "inst_misc.cu", "inst_run.cu", "inst_coop.cu"]
+    srcs = HEADERS + COOP_HEADERS + ["qekf_capi.cu", "inst_misc.cu", "inst_run.cu", "inst_coop.cu", "inst_duo.cu"]
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in srcs)
 
 
 def _deps(src):
-    return [src] + HEADERS + (COOP_HEADERS if src == "inst_coop.cu" else [])
+    return [src] + HEADERS + (COOP_HEADERS if src in ("inst_coop.cu", "inst_duo.cu") else [])
 
 
 def _compile(unit, verbose, force=False):

@@ -925,12 +925,17 @@ struct GroupSync {
     int id;                  // device: named barrier 1..15
     void (*fn)(void *);      // host harness: thread barrier
     void *ctx;
+    int nthreads = 96;       // device: threads that meet at the barrier
 #ifdef __CUDA_ARCH__
-    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
     __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+    // CTA-wide "does anybody still ...": one barrier per loop iteration, which also keeps the groups of a CTA within
+    // one iteration of each other so that they share the instruction cache lines of the (large, unrolled) tick
+    __device__ __forceinline__ bool cta_any(bool x) const { return __syncthreads_or(x) != 0; }
 #else
     void sync() const { fn(ctx); }
     void cta_sync() const { fn(ctx); }
+    bool cta_any(bool x) const { return x; }
 #endif
 };
 
@@ -1291,7 +1296,7 @@ __global__ void __launch_bounds__(96 * G, 1) run_kernel_coop(const __grid_consta
     __syncthreads();
     PLane<T, NB, F> P;
     P.setup(sm + f, c);
-    const GroupSync gs{ g + 1, nullptr, nullptr };
+    const GroupSync gs{ g + 1, nullptr, nullptr, 96 };
     const CtaCtx<T> cta{ g, G, sm + (size_t)Lay<NB>::CB * F };
     const bool live = i < a.st.n;
     const SPtr<T> rc = SPtr<T>::from(rcs + c * RC_N);

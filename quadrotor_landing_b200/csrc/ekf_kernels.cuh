@@ -374,6 +374,38 @@ QEKF_FN CtaVote cta_vote(int *vbuf, uint32_t iter, bool active, bool want, bool 
     return r;
 }
 
+// Warp-level votes.  Time skew and the statistics fence only need agreement among lanes that execute together, i.e.
+// the 32 lanes of a warp: five ballots, no shared memory, no atomics.  The CTA still meets once per iteration
+// (cta_any) so that its warps walk the instruction stream together and the loop ends for all of them at once.
+struct WarpVote {
+    int active, want, fenced, at_fence, lanes;
+    bool out_of_patience;
+};
+QEKF_FN WarpVote warp_vote(bool active, bool want, bool oop, bool fenced, bool at_fence)
+{
+    WarpVote r;
+#ifdef __CUDA_ARCH__
+    const unsigned full = 0xffffffffu;
+    r.active = __popc(__ballot_sync(full, active));
+    r.want = __popc(__ballot_sync(full, want));
+    r.fenced = __popc(__ballot_sync(full, fenced));
+    r.at_fence = __popc(__ballot_sync(full, at_fence));
+    r.out_of_patience = __ballot_sync(full, oop) != 0u;
+    r.lanes = 32;
+#else
+    r.active = active; r.want = want; r.fenced = fenced; r.at_fence = at_fence; r.out_of_patience = oop; r.lanes = 1;
+#endif
+    return r;
+}
+QEKF_FN bool cta_any(bool x)
+{
+#ifdef __CUDA_ARCH__
+    return __syncthreads_or(x) != 0;
+#else
+    return x;
+#endif
+}
+
 // The per-filter replay loop, one lane per filter.  Host-callable so that the CPU-side unit tests
 // (tests/host_core) can run the very same code against the oracle without a GPU; the product only ever
 // calls it from run_kernel.
@@ -445,8 +477,8 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
-        if (v.active == 0 && v.at_fence == 0) break;     // every lane of the CTA has finished
+        const WarpVote v = warp_vote(active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (!cta_any(active || at_fence)) break;         // every lane of the CTA has finished
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // every lane is at the fence (or finished): sample together, then resume on the next iteration
@@ -685,8 +717,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
-        if (v.active == 0 && v.at_fence == 0) break;
+        const WarpVote v = warp_vote(active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (!cta_any(active || at_fence)) break;
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // look at the head: park the checkpoint, replay the nh implied predictions, sample, come back

@@ -16,4 +16,10 @@ bool coop_groups_available(int groups, bool bench_variant);
 template <bool BIAS, bool DIRECT, bool SYNTH, bool PF>
 cudaError_t launch_run_coop(const RunArgs<double> &a, int groups, cudaStream_t stream);
 
+// the two-role kernel of ekf_duo.cuh (two warps per 32 filters), instantiated in inst_duo.cu
+constexpr int DUO_GROUPS_DEFAULT = 6;
+bool duo_groups_available(int groups, bool bench_variant);
+template <bool BIAS, bool DIRECT, bool SYNTH, bool PF>
+cudaError_t launch_run_duo(const RunArgs<double> &a, int groups, cudaStream_t stream);
+
 }  // namespace qekf

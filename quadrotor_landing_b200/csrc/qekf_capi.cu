@@ -83,9 +83,10 @@ struct qekf_handle {
     size_t d_mask_bytes = 0;
     // launch bookkeeping
     int64_t launches = 0;
-    // mapping of the fused replay (qekf_set_mapping): 3 = cooperative kernel where it exists (FP64, single-rate)
-    int lanes_per_filter = 3;
-    int coop_groups = COOP_GROUPS_DEFAULT;
+    // mapping of the fused replay (qekf_set_mapping), where the kernels exist (FP64, single-rate): 2 = two role-specialised
+    // warps per 32 filters (ekf_duo.cuh), 3 = three lanes per filter (ekf_coop.cuh), 1 = one thread per filter
+    int lanes_per_filter = 1;
+    int coop_groups = COOP_GROUPS_DEFAULT, duo_groups = DUO_GROUPS_DEFAULT;
 };
 
 namespace {
@@ -271,6 +272,17 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
     }
     const bool mr = h->p.multirate_ekf != 0, pf = h->pf_on;
     if constexpr (std::is_same<T, double>::value) {
+        if (!mr && h->lanes_per_filter == 2) {
+            // two role-specialised warps per 32 filters (ekf_duo.cuh)
+            cudaError_t e;
+            if (ns) e = pf ? launch_run_duo<BIAS, DIRECT, true, true>(a, h->duo_groups, h->stream)
+                           : launch_run_duo<BIAS, DIRECT, true, false>(a, h->duo_groups, h->stream);
+            else e = pf ? launch_run_duo<BIAS, DIRECT, false, true>(a, h->duo_groups, h->stream)
+                        : launch_run_duo<BIAS, DIRECT, false, false>(a, h->duo_groups, h->stream);
+            if (e != cudaSuccess) return fail(QEKF_ERR_CUDA, std::string("two-role replay launch: ") + cudaGetErrorString(e));
+            h->launches++;
+            return QEKF_OK;
+        }
         if (!mr && h->lanes_per_filter == 3) {
             // three lanes per filter (ekf_coop.cuh)
             cudaError_t e;
@@ -476,9 +488,11 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
     h->p = *p; h->precision = precision; h->device = device;
     {   // environment overrides of the default mapping (profiling / A-B runs): QEKF_LANES=1|3, QEKF_COOP_GROUPS=n
         const char *e = getenv("QEKF_LANES");
-        if (e && (atoi(e) == 1 || atoi(e) == 3)) h->lanes_per_filter = atoi(e);
+        if (e && atoi(e) >= 1 && atoi(e) <= 3) h->lanes_per_filter = atoi(e);
         e = getenv("QEKF_COOP_GROUPS");
         if (e && coop_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->coop_groups = atoi(e);
+        e = getenv("QEKF_DUO_GROUPS");
+        if (e && duo_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->duo_groups = atoi(e);
     }
     h->n = n_filters; h->ld = (n_filters + 31) / 32 * 32;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -585,13 +599,18 @@ int64_t qekf_num_filters(const qekf_handle *h) { return h ? h->n : 0; }
 int qekf_set_mapping(qekf_handle *h, int lanes_per_filter, int groups)
 {
     if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
-    if (lanes_per_filter != 1 && lanes_per_filter != 3) return fail(QEKF_ERR_BAD_ARG, "lanes_per_filter must be 1 or 3");
-    if (groups == 0) groups = COOP_GROUPS_DEFAULT;
+    if (lanes_per_filter < 1 || lanes_per_filter > 3) return fail(QEKF_ERR_BAD_ARG, "lanes_per_filter must be 1, 2 or 3");
+    const bool bench_variant = h->p.est_bias && h->p.direct_orien_method && !h->pf_on;
     if (lanes_per_filter == 3) {
-        const bool bench_variant = h->p.est_bias && h->p.direct_orien_method && !h->pf_on;
+        if (groups == 0) groups = COOP_GROUPS_DEFAULT;
         if (!coop_groups_available(groups, bench_variant))
-            return fail(QEKF_ERR_BAD_ARG, "this build has no cooperative kernel with that many groups per CTA for this filter variant");
+            return fail(QEKF_ERR_BAD_ARG, "this build has no three-lane kernel with that many groups per CTA for this filter variant");
         h->coop_groups = groups;
+    } else if (lanes_per_filter == 2) {
+        if (groups == 0) groups = DUO_GROUPS_DEFAULT;
+        if (!duo_groups_available(groups, bench_variant))
+            return fail(QEKF_ERR_BAD_ARG, "this build has no two-role kernel with that many groups per CTA for this filter variant");
+        h->duo_groups = groups;
     }
     h->lanes_per_filter = lanes_per_filter;
     return QEKF_OK;

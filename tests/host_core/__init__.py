@@ -222,7 +222,7 @@ def count_flops(params):
 _COOP_LIB = os.path.join(_HERE, "libhost_coop.so")
 _COOP_SRC = [os.path.join(_HERE, "host_coop.cu")] + [
     os.path.join(_HERE, "..", "..", "quadrotor_landing_b200", "csrc", f)
-    for f in ("ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_coop.cuh", "ekf_params.hpp")
+    for f in ("ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_coop.cuh", "ekf_duo.cuh", "ekf_params.hpp")
 ]
 _coop = None
 
@@ -267,6 +267,8 @@ class CoopHostBatch(HostBatch):
     """N filters advanced by the product's run_filter_coop() on the host: three threads per filter meeting at a barrier,
     every shared word traced.  FP64, single-rate.  self.races = races seen by the tracer in the last run."""
 
+    ENTRY = "hcoop_run"
+
     def __init__(self, params, n_filters):
         assert not params.multirate_ekf
         super().__init__(params, n_filters, 64)
@@ -275,12 +277,13 @@ class CoopHostBatch(HostBatch):
     def _call(self, k0, n_steps, imu, step, pose, stamp, valid, t_start, noise, truth, stats, stride):
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L = coop_lib()
-        L.hcoop_run.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, C.POINTER(C.c_uint8),
+        fn = getattr(L, self.ENTRY)
+        fn.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, C.POINTER(C.c_uint8),
                                  C.c_double] + [dp] * 4 + [ip] * 2 + [C.c_void_p, dp, dp, C.c_int32, C.c_int32] + [dp] * 6)
         vptr = valid.ctypes.data_as(C.POINTER(C.c_uint8)) if valid is not None else None
         pf = [_dp(a) for a in self.pf] if self.pf is not None else [None] * 5
         diag = np.zeros(2)
-        L.hcoop_run(C.byref(self.p), self.N, int(k0), int(n_steps), _dp(imu), step.shape[0], step.ctypes.data_as(ip),
+        fn(C.byref(self.p), self.N, int(k0), int(n_steps), _dp(imu), step.shape[0], step.ctypes.data_as(ip),
                     _dp(pose), _dp(stamp), vptr, float(t_start), _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
                     self.flags.ctypes.data_as(ip), self.upds.ctypes.data_as(ip),
                     C.byref(noise) if noise is not None else None, _dp(truth) if truth is not None else None,
@@ -300,3 +303,9 @@ class CoopHostBatch(HostBatch):
         imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
         step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
         self._call(k0, n_steps, imu, step, pose, stamp, None, scn.spec.t_start, noise, truth, stats, stride)
+
+
+class DuoHostBatch(CoopHostBatch):
+    """N filters advanced by the product's run_filter_duo() on the host: two threads per filter (role A: covariance core
+    and corrections, role B: nominal state and bias columns) meeting at a barrier.  FP64, single-rate."""
+    ENTRY = "hduo_run"

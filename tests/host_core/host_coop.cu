@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../quadrotor_landing_b200/csrc/ekf_coop.cuh"
+#include "../../quadrotor_landing_b200/csrc/ekf_duo.cuh"
 #include "../../quadrotor_landing_b200/csrc/ekf_params.hpp"
 
 using namespace qekf;
@@ -211,7 +212,7 @@ template <bool BIAS, bool DIRECT> void coop_correct_t(const qekf_params *p, int 
 // ---- the full replay loop: three threads per filter meeting at a barrier ---------------------------
 struct Bar3 {
     pthread_barrier_t b;
-    Bar3() { pthread_barrier_init(&b, nullptr, 3); }
+    explicit Bar3(int n = 3) { pthread_barrier_init(&b, nullptr, n); }
     ~Bar3() { pthread_barrier_destroy(&b); }
     static void wait(void *ctx)
     {
@@ -326,9 +327,119 @@ void coop_run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, co
     diag[1] = spread;
 }
 
+// ---- the two-role mapping (ekf_duo.cuh): two threads per filter ---------------------------------------
+template <bool BIAS, bool DIRECT>
+void duo_run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
+               const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
+               double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+               const McArgs *mc, const double *const *pf, double *diag)
+{
+    constexpr int NS = BIAS ? 15 : 9, NP = NS * (NS + 1) / 2;
+    RunArgs<double> a;
+    std::memset(&a, 0, sizeof a);
+    a.st.x = x; a.st.P = Ppk; a.st.aux = aux; a.st.pend = pend;
+    a.st.flags = flags; a.st.upds = upds; a.st.counts = nullptr; a.st.ld = N; a.st.n = N;
+    a.in.imu = imu; a.in.tag_step = tag_step; a.in.tag_pose = tag_pose; a.in.tag_stamp = tag_stamp;
+    a.in.tag_valid = tag_valid; a.in.cs = N; a.in.is = 1; a.in.M = M; a.in.vs = N;
+    a.in.t_start = t_start; a.in.update_freq = p->update_freq;
+    a.c = make_consts<double>(*p);
+    a.k0 = k0; a.n_steps = n_steps;
+    int32_t m0 = 0;
+    while (m0 < M && tag_step[m0] < k0) ++m0;
+    a.m0 = m0;
+    std::vector<uint8_t> mask;
+    std::vector<double> sig;
+    const bool synth = mc && mc->ns;
+    if (synth) {
+        a.in.cs = 1; a.in.is = 0; a.in.vs = 0; a.in.tag_valid = nullptr;
+        a.ns = *mc->ns;
+        if (a.ns.edge_loss) {
+            mask.resize((size_t)M);
+            visibility_mask(tag_pose, M, make_consts<double>(*p), mask.data());
+            a.in.tag_valid = mask.data();
+        }
+        if (a.ns.range_ref > 0) {
+            sig.resize((size_t)M * 2);
+            range_sigmas(tag_pose, M, a.ns, sig.data());
+            a.in.tag_sigma = sig.data();
+        }
+        if (mc->stats_acc && mc->truth) {
+            a.stats.acc = mc->stats_acc; a.stats.truth = mc->truth; a.stats.n_bins = mc->n_bins; a.stats.stride = mc->stride;
+            a.stats.chi2_lo = BIAS ? 6.262137795043251 : 2.7003894999803584;
+            a.stats.chi2_hi = BIAS ? 27.488392863442982 : 19.02276779864163;
+        }
+    }
+    std::vector<double> pft, pfd;
+    const bool has_pf = pf && pf[0];
+    if (has_pf) {
+        pft.assign((size_t)PF_DIM * N, 0.0);
+        pfd.assign(2 * (size_t)N, 0.0);
+        qekf_params q = *p;
+        for (int64_t i = 0; i < N; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                q.Q_a[k] = pf[0][(0 + k) * N + i]; q.Q_w[k] = pf[0][(3 + k) * N + i];
+                q.Q_ab[k] = pf[0][(6 + k) * N + i]; q.Q_wb[k] = pf[0][(9 + k) * N + i];
+                q.R_r[k] = pf[1][(0 + k) * N + i]; q.R_ang[k] = pf[1][(3 + k) * N + i];
+                q.r_v_cv[k] = pf[2][k * N + i];
+            }
+            for (int k = 0; k < 4; ++k) q.q_vc[k] = pf[3][k * N + i];
+            fill_pf_column<double>(q, pft.data() + i, N);
+            pfd[i] = pf[4][i]; pfd[N + i] = pf[4][N + i];
+        }
+        a.st.pf = pft.data(); a.st.pf_delay = pfd.data();
+    }
+    for (int64_t i = 0; i < N; ++i) {
+        std::vector<double> pk(NP, std::nan("")), xw(duo::X_WORDS, std::nan(""));
+        Bar3 bar(2);
+        auto role_main = [&](int role) {
+            PShared<double, NS, 1> P{ pk.data() };
+            const duo::XBuf<double, 1> X{ xw.data() };
+            GroupSync gs{ 0, &Bar3::wait, &bar, 2 };
+#define DUO_(S, F) duo::run_filter_duo<double, BIAS, DIRECT, S, F>(a, i, P, X, role, true, gs)
+            if (synth && has_pf) DUO_(true, true);
+            else if (synth) DUO_(true, false);
+            else if (has_pf) DUO_(false, true);
+            else DUO_(false, false);
+#undef DUO_
+        };
+        std::thread tb(role_main, (int)duo::ROLE_B);
+        role_main((int)duo::ROLE_A);
+        tb.join();
+    }
+    diag[0] = 0;
+    diag[1] = 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+void hduo_run(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
+              const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
+              double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
+              const qekf_noise_spec *n, const double *truth, double *stats_acc, int32_t n_bins, int32_t stride,
+              const double *pf_q, const double *pf_r, const double *pf_rvcv, const double *pf_qvc, const double *pf_delay,
+              double *diag)
+{
+    NoiseSpec ns;
+    McArgs mc = { nullptr, truth, stats_acc, n_bins, stride };
+    if (n) {
+        std::memset(&ns, 0, sizeof ns);
+        ns.seed = n->seed; ns.gid0 = n->first_global_id;
+        ns.sig_a = (float)n->sigma_accel; ns.sig_w = (float)n->sigma_gyro;
+        ns.sig_ba = (float)n->sigma_bias_accel; ns.sig_bw = (float)n->sigma_bias_gyro;
+        ns.sig_p = (float)n->sigma_tag_pos; ns.sig_th = (float)n->sigma_tag_ang;
+        ns.drop_k0 = n->dropout_k0; ns.drop_k1 = n->dropout_k1;
+        ns.rdrop_len = n->rand_dropout_len; ns.rdrop_lo = n->rand_dropout_lo; ns.rdrop_hi = n->rand_dropout_hi;
+        ns.edge_loss = n->edge_loss; ns.range_ref = n->range_ref; ns.range_exp_p = n->range_exp_pos; ns.range_exp_th = n->range_exp_ang;
+        mc.ns = &ns;
+    }
+    const double *pf[5] = { pf_q, pf_r, pf_rvcv, pf_qvc, pf_delay };
+    const bool b = p->est_bias != 0, d = p->direct_orien_method != 0;
+#define C_(B, D) duo_run_t<B, D>(p, N, k0, n_steps, imu, M, tag_step, tag_pose, tag_stamp, tag_valid, t_start, x, Ppk, aux, pend, flags, upds, &mc, pf, diag)
+    if (b && d) C_(true, true); else if (b) C_(true, false); else if (d) C_(false, true); else C_(false, false);
+#undef C_
+}
 
 // state arrays as hc_run (x [16][N], Ppk [NP][N] packed, aux [11][N], pend [8][N], flags [N], upds [N]); FP64, single-rate.
 // ns == NULL: explicit streams.  pf_*: per-filter overrides or all NULL.
