@@ -259,7 +259,7 @@ enum { ROLE_A = 0, ROLE_B = 1 };
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS, class XB>
 QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, const XB &X, const int role, const bool live,
-                            const GroupSync gs)
+                            const GroupSync gs, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
@@ -317,7 +317,8 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
         kin_publish(s, accel, u, c, X);
     };
 
-    for (;;) {
+    cta_vote_init(vbuf);
+    for (uint32_t iter = 0;; ++iter) {
         const bool active = (k < k_end) && !at_fence;
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
@@ -344,8 +345,10 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
 
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const GroupVote v = group_vote(active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
-        if (!gs.cta_any(active || at_fence)) break;      // every lane of the CTA has finished (lockstep point)
+        // CTA-wide vote (one barrier per iteration): all groups of the CTA serve their corrections in the same
+        // iteration and walk the instruction stream together
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // every filter of the group is at the sampling point (or finished).  Role B never runs ahead across a
@@ -502,12 +505,13 @@ __global__ void __launch_bounds__(64 * G, 1) run_kernel_duo(const __grid_constan
     const int64_t i = (int64_t)blockIdx.x * F + f;
     PShared<T, N, F> P{ sm + f };
     const XBuf<T, F> X{ sm + (size_t)NP * F + f };
+    int *vbuf = reinterpret_cast<int *>(sm + (size_t)(NP + X_WORDS) * F);
     const GroupSync gs{ g + 1, nullptr, nullptr, 64 };
-    run_filter_duo<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, X, role, i < a.st.n, gs);
+    run_filter_duo<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, X, role, i < a.st.n, gs, vbuf);
 }
 template <int N> constexpr size_t duo_smem_bytes(int groups, size_t tsize)
 {
-    return ((size_t)(N * (N + 1) / 2) + X_WORDS) * 32 * groups * tsize;
+    return ((size_t)(N * (N + 1) / 2) + X_WORDS) * 32 * groups * tsize + VOTE_WORDS * sizeof(int);
 }
 #endif
 

@@ -374,9 +374,10 @@ QEKF_FN CtaVote cta_vote(int *vbuf, uint32_t iter, bool active, bool want, bool 
     return r;
 }
 
-// Warp-level votes.  Time skew and the statistics fence only need agreement among lanes that execute together, i.e.
-// the 32 lanes of a warp: five ballots, no shared memory, no atomics.  The CTA still meets once per iteration
-// (cta_any) so that its warps walk the instruction stream together and the loop ends for all of them at once.
+// Warp-level votes (five ballots, no shared memory).  Measured and NOT used by the thread-per-filter loops: when every
+// warp decides for itself, the warps of a CTA serve their corrections in different iterations, and since the CTA
+// meets once per iteration (lockstep keeps the instruction cache shared) everybody pays for every warp's correction:
+// 4.21e9 vs 4.68e9 filter-steps/s with the CTA-wide vote (profiles/r2_04_mappings.md).
 struct WarpVote {
     int active, want, fenced, at_fence, lanes;
     bool out_of_patience;
@@ -477,8 +478,8 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const WarpVote v = warp_vote(active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
-        if (!cta_any(active || at_fence)) break;         // every lane of the CTA has finished
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;     // every lane of the CTA has finished
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // every lane is at the fence (or finished): sample together, then resume on the next iteration
@@ -717,8 +718,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 
         const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
-        const WarpVote v = warp_vote(active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
-        if (!cta_any(active || at_fence)) break;
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // look at the head: park the checkpoint, replay the nh implied predictions, sample, come back
