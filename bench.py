@@ -125,19 +125,19 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
 
 
-def cpu_streams(q, scn, n_filters):
+def cpu_streams(noise, scn, n_filters, first=0):
     """Explicit noisy streams for the CPU legs (same noise model and seeds, numpy restatement of the generator)."""
     from oracle import noise_np
-    st = noise_np.synthesize(bench_noise(q), scn.imu_clean, scn.tag_step, scn.tag_pose_clean, np.arange(n_filters))
+    st = noise_np.synthesize(noise, scn.imu_clean, scn.tag_step, scn.tag_pose_clean, np.arange(first, first + n_filters))
     return np.ascontiguousarray(st["imu"]), np.ascontiguousarray(st["tag_pose"]), st["tag_valid"]
 
 
-def cpu_replay(p, scn, streams, threads):
+def cpu_replay(op, scn, streams, threads):
     """One bounded CPU step: the dense restatement of the reference (oracle/) replays the whole scenario for
-    the sample's filters, OpenMP over filters.  Returns seconds."""
+    the sample's filters, OpenMP over filters.  `op`: oracle parameter struct.  Returns seconds."""
     from oracle import ekf_oracle as orc
     imu, pose, valid = streams
-    ob = orc.Batch(orc.params_from(p), imu.shape[2])
+    ob = orc.Batch(op, imu.shape[2])
     t0 = time.perf_counter()
     ob.run(0, scn.T, imu, scn.tag_step, pose, scn.tag_stamp, valid, n_threads=threads)
     return time.perf_counter() - t0
@@ -147,28 +147,31 @@ CPU_NOTE = ("dense C restatement of relative_pose_EKF.cpp (oracle/ekf_oracle.c),
             "the reference's own C++ needs Eigen >= 3.4, which is absent, so it cannot be built here")
 
 
+def cpu_sample_filters(threads):
+    return max(32, 32 * threads)
+
+
 def run_reference(args):
     """--impl reference: the reference's own algorithm on the host cores, same scenario / noise / parameters.
-    Rank 0 only; the other ranks exit without work."""
+    Rank 0 only; the other ranks exit without work.  Loads oracle/ libraries only -- not the product package."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import quadrotor_landing_b200 as q
-    from quadrotor_landing_b200 import scenario
-    p = bench_params(q, args.multirate, args.dynamic_delay)
-    scn = bench_scenario(q, p)          # host-only C++ generator inside libqekf (no GPU needed)
+    from oracle import bench_ref
+    op = bench_ref.params(args.multirate, args.dynamic_delay)
+    scn = bench_ref.scenario(op, 0.030 if args.multirate else 0.0)
     threads = os.cpu_count() or 1
-    sample = max(32, 32 * threads)
-    streams = cpu_streams(q, scn, sample)
+    sample = cpu_sample_filters(threads)
+    streams = cpu_streams(bench_ref.noise(), scn, sample)
     for _ in range(args.warmup):
-        cpu_replay(p, scn, streams, threads)
-    times = [cpu_replay(p, scn, streams, threads) for _ in range(args.steps)]
+        cpu_replay(op, scn, streams, threads)
+    times = [cpu_replay(op, scn, streams, threads) for _ in range(args.steps)]
     dt = float(np.mean(times))
     rate = sample * scn.T / dt
     line = {
         "impl": "reference", "metric": "EKF filter-steps/s (propagate+update)", "value": rate, "unit": "filter-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, scn),
+        "config": workload_config(args, scn, sample),
         "cpu_baseline": {"value": rate, "unit": "filter-steps/s", "cores": threads, "kind": "port",
                          "sample": "%d filters x %d ticks per step; %s" % (sample, scn.T, CPU_NOTE)},
         "e2e": {"value": rate, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -176,28 +179,202 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, scn):
+def workload_config(args, scn, cpu_sample=None):
     mode = "single-rate"
     if getattr(args, "sweep", False):
         mode = "per-filter Q/R/camera-extrinsic sweep, " + mode
     if args.multirate:
         mode = mode.replace("single-rate", "") + "delayed-fusion (multirate_ekf, %s delay, 30 ms tag latency)" % (
             "dynamic" if args.dynamic_delay else "fixed 30 ms")
-    return {"workload": "Monte-Carlo replay of a 60 s hover-and-descend landing: %d filters per GPU x %d ticks "
-                        "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), %s direct-orientation "
-                        "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T, mode),
-            "filters_per_gpu": args.filters, "ticks": int(scn.T), "tag_arrivals": int(scn.M),
-            "precision": "fp64" if args.precision == 64 else "fp32",
-            "l2": "per-filter state (1.1 GB per 1M filters) is far larger than L2 and is re-read every step; the "
-                  "shared clean scenario (0.7 MB) is L2-resident by design",
-            "parallelism": "filters sharded over %d GPU(s), NCCL all-reduce of the statistics" % args.gpus}
+    cfg = {"workload": "Monte-Carlo replay of a 60 s hover-and-descend landing: %d filters per GPU x %d ticks "
+                       "(200 Hz IMU, 30 Hz tag, 2 s common + 1 s per-filter tag dropout), %s direct-orientation "
+                       "EKF, est_bias, rotors.yaml noises" % (args.filters, scn.T, mode),
+           "filters_per_gpu": args.filters, "ticks": int(scn.T), "tag_arrivals": int(scn.M),
+           "precision": "fp64" if args.precision == 64 else "fp32",
+           "l2": "per-filter state (1.1 GB per 1M filters) is far larger than L2 and is re-read every step; the "
+                 "shared clean scenario (0.7 MB) is L2-resident by design",
+           "parallelism": "filters sharded over %d GPU(s), NCCL all-reduce of the statistics" % args.gpus}
+    if cpu_sample is not None:
+        # the CPU legs time a bounded SAMPLE of the same workload (same scenario, noise model and parameters)
+        cfg["cpu_sample_filters"] = int(cpu_sample)
+    return cfg
+
+
+class Leg:
+    """One workload variant on this rank's GPU: a handle, its device-resident inputs and the timed pass."""
+
+    def __init__(self, q, torch, local, rank, world, n_filters, precision=64, multirate=False, dynamic=False, sweep=False,
+                 no_stats=False, no_private_dropout=False):
+        from quadrotor_landing_b200.sharded import shard_range
+        self.q, self.torch, self.local, self.rank, self.world = q, torch, local, rank, world
+        self.dev = torch.device("cuda", local)
+        self.p = bench_params(q, multirate, dynamic)
+        self.scn = bench_scenario(q, self.p)
+        self.T, self.M, self.N = self.scn.T, self.scn.M, n_filters
+        self.prec = q.QEKF_FP64 if precision == 64 else q.QEKF_FP32
+        self.first_id, n_local = shard_range(n_filters * world, rank, world)     # every GPU owns n_filters filters
+        assert n_local == n_filters
+        self.noise = bench_noise(q, first_global_id=self.first_id)
+        if no_private_dropout:
+            self.noise.rand_dropout_len = 0
+        self.stride = 200                              # one statistics sample per simulated second
+        self.nb = self.T // self.stride
+        self.b = q.BatchEKF(self.p, n_filters, device=local, precision=self.prec)
+        self.stream = torch.cuda.current_stream()
+        self.b.set_stream(self.stream.cuda_stream)
+        if sweep:
+            apply_sweep(q, self.b, self.p, n_filters, seed=1234 + rank)
+        self.b.stats_configure(self.nb, self.stride if not no_stats else 10 ** 9)
+        self.stats_dev = torch.zeros((self.nb, q.STAT_DIM), dtype=torch.float64, device=self.dev)
+        scn, dev = self.scn, self.dev
+        # device-resident inputs (the `value` leg)
+        self._keep = [torch.tensor(scn.imu_clean, device=dev), torch.tensor(scn.tag_pose_clean, device=dev),
+                      torch.tensor(scn.tag_stamp, device=dev), torch.tensor(scn.tag_step, dtype=torch.int32, device=dev),
+                      torch.tensor(scn.truth, device=dev)]
+        self.sh = self._shared(self._keep, 1)
+        self.h_stats = np.zeros((self.nb, q.STAT_DIM))
+
+    def _shared(self, t, on_device):
+        sh = self.q.QekfSharedStreams()
+        sh.T, sh.imu_clean, sh.M = self.T, t[0].data_ptr(), self.M
+        sh.tag_pose_clean, sh.tag_stamp, sh.tag_step = t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr()
+        sh.truth, sh.t_start, sh.on_device = t[4].data_ptr(), 0.0, on_device
+        return sh
+
+    def host_inputs(self):
+        """pinned host copies of the shared scenario (the `e2e` leg); returns (shared view, bytes)"""
+        torch, scn = self.torch, self.scn
+        t = [torch.tensor(scn.imu_clean).pin_memory(), torch.tensor(scn.tag_pose_clean).pin_memory(),
+             torch.tensor(scn.tag_stamp).pin_memory(), torch.tensor(scn.tag_step, dtype=torch.int32).pin_memory(),
+             torch.tensor(scn.truth).pin_memory()]
+        self._keep_host = t
+        nbytes = sum(x.numel() * x.element_size() for x in t)
+        return self._shared(t, 0), nbytes
+
+    def one_step(self, shared, host_result):
+        """One pass of the hot path: reset -> fused replay of all T ticks -> statistics (all-reduced at N>1)."""
+        from quadrotor_landing_b200.sharded import all_reduce_stats
+        b = self.b
+        b.reset_filters()
+        b.stats_reset()
+        b.run_monte_carlo_device(shared, self.noise, 0, self.T)
+        b.copy_stats_device(self.stats_dev.data_ptr())
+        all_reduce_stats(self.stats_dev)                 # NCCL sum over the ranks (no-op at N=1)
+        if host_result:
+            self.h_stats[:] = self.stats_dev.cpu().numpy()
+
+    def barrier(self, dist):
+        if dist is not None:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, shared, host_result, steps, dist):
+        torch = self.torch
+        self.barrier(dist)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            self.one_step(shared, host_result)
+        e1.record(self.stream)
+        self.barrier(dist)
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if host_result:
+            ms = max(ms, wall * 1e3)          # the host-visible time is what a caller of the C ABI sees
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def kernel_ms(self, reps=2):
+        """The fused kernel alone (for the roofline): events around the launch only, on its stream."""
+        torch, b = self.torch, self.b
+        out = []
+        for _ in range(reps):
+            b.reset_filters(); b.stats_reset()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            b.run_monte_carlo_device(self.sh, self.noise, 0, self.T)
+            e1.record(self.stream)
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return float(np.mean(out))
+
+    def roofline(self, k_ms, n_pred, n_corr, peak):
+        """Executed flops of one launch / kernel time against the self-measured FMA peak of the precision."""
+        q, p = self.q, self.p
+        fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
+        if self.prec == q.QEKF_FP32:
+            fc += JOSEPH_EXTRA_FLOPS[int(p.est_bias)]      # the FP32 mode's refined gain (Joseph form), DESIGN.md section 7
+        flops = n_pred * fp + n_corr * fc
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        return {"bound": "fp64" if self.prec == q.QEKF_FP64 else "fp32", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "peak_source": "self-measured FMA microbenchmark in this run (qekf_measure_fma_peak); "
+                               "MEASURED_PEAKS.json has no CUDA-core figure",
+                "kernel": "run_kernel", "kernel_ms": k_ms,
+                "flops_per_filter_step": flops / (self.N * self.T),
+                "work": {"prediction_steps": n_pred, "correction_steps": n_corr,
+                         "flops_per_prediction": fp, "flops_per_correction": fc}}
+
+    def parity(self, windows=3, width=64):
+        """Max norm-relative deviation of this rank's filters from the oracle, on `windows` id windows (first, middle,
+        last) of `width` filters: the device dumps the noise realisation of the window (qekf_synthesize_streams), the
+        oracle replays it, and state / covariance after the last tick are compared with what the timed pass left on the
+        device.  Outside any timed region."""
+        from oracle import ekf_oracle as orc
+        b, scn, N = self.b, self.scn, self.N
+        op = orc.params_from(self.p)
+        starts = sorted({0, max(0, (N - width) // 2), max(0, N - width)})[:windows]
+        ex = eP = 0.0
+        for f0 in starts:
+            w = min(width, N - f0)
+            st = b.synthesize_streams(scn, self.noise, f0, w)
+            ob = orc.Batch(op, w)
+            ob.run(0, self.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+            xo, Po = ob.state(), ob.cov()
+            xg, Pg = b.state(f0, w), b.cov(f0, w)
+            ex = max(ex, float(np.max(np.abs(xg - xo)) / np.max(np.abs(xo))))
+            eP = max(eP, float(np.max(np.abs(Pg - Po)) / np.max(np.abs(Po))))
+        return {"state_norm_rel": ex, "cov_norm_rel": eP, "filters_checked": int(len(starts) * width),
+                "windows_first_local_id": [int(x) for x in starts], "first_global_id": int(self.first_id),
+                "tolerance": 1e-9 if self.prec == self.q.QEKF_FP64 else 1e-4,
+                "against": "oracle/ekf_oracle.c replaying the device's dumped noise realisation (FP64)"}
+
+    def close(self):
+        self.b.close()
+        self._keep = None
+        self.torch.cuda.empty_cache()
+
+
+def run_leg(q, torch, nat, local, rank, world, dist, n_filters, steps, **kw):
+    """A secondary workload variant, timed the same way as the main line (device-resident inputs), 1 warm-up pass."""
+    leg = Leg(q, torch, local, rank, world, n_filters, **kw)
+    leg.one_step(leg.sh, False)
+    torch.cuda.synchronize()
+    leg.b.step_counts(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = leg.timed(leg.sh, False, steps, dist) / steps
+    n_pred, n_corr = leg.b.step_counts(reset=True)
+    clocks = sampler.stop()
+    k_ms = leg.kernel_ms(1)
+    peak = nat.measure_fma_peak(local, leg.prec)
+    out = {"value": n_filters * leg.T * world / (ms * 1e-3), "unit": "filter-steps/s", "steps": steps, "ms_per_step": ms,
+           "dtype": "f64" if leg.prec == q.QEKF_FP64 else "f32",
+           "roofline": leg.roofline(k_ms, n_pred / steps, n_corr / steps, peak), "clocks": clocks}
+    if kw.get("precision", 64) == 32:
+        out["parity"] = leg.parity(windows=1)
+    leg.close()
+    return out
 
 
 def run_ours(args):
     import torch
     import quadrotor_landing_b200 as q
     from quadrotor_landing_b200 import _native as nat
-    from quadrotor_landing_b200 import scenario
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,113 +386,64 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) out of it
-        os.environ["NCCL_DEBUG"] = os.environ.get("QEKF_NCCL_DEBUG", "WARN")
+        # stdout carries exactly one JSON line.  NCCL's own log (communicator init: "... nranks N ...") is evidence the
+        # driver wants, so it is not silenced: it goes to stderr, at INFO for the INIT subsystem unless the
+        # environment already says otherwise.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
-    p = bench_params(q, args.multirate, args.dynamic_delay)
-    scn = bench_scenario(q, p)
-    T, M = scn.T, scn.M
     N = args.filters
-    prec = q.QEKF_FP64 if args.precision == 64 else q.QEKF_FP32
-    from quadrotor_landing_b200.sharded import all_reduce_stats, shard_range
-    first_id, n_local = shard_range(N * world, rank, world)     # weak scaling: N filters per GPU
-    assert n_local == N
-    noise = bench_noise(q, first_global_id=first_id)
-    if args.no_private_dropout:
-        noise.rand_dropout_len = 0
-    stride = 200                                   # one statistics sample per simulated second
-    nb = T // stride
-
-    b = q.BatchEKF(p, N, device=local, precision=prec)
-    stream = torch.cuda.current_stream()
-    b.set_stream(stream.cuda_stream)
-    if args.sweep:
-        apply_sweep(q, b, p, N, seed=1234 + rank)
-    b.stats_configure(nb, stride if not args.no_stats else 10 ** 9)
-    stats_dev = torch.zeros((nb, q.STAT_DIM), dtype=torch.float64, device=dev)
-
-    # ---- device-resident inputs (the `value` leg) ----
-    d_imu = torch.tensor(scn.imu_clean, device=dev)
-    d_pose = torch.tensor(scn.tag_pose_clean, device=dev)
-    d_stamp = torch.tensor(scn.tag_stamp, device=dev)
-    d_step = torch.tensor(scn.tag_step, dtype=torch.int32, device=dev)
-    d_truth = torch.tensor(scn.truth, device=dev)
-    sh = q.QekfSharedStreams()
-    sh.T, sh.imu_clean, sh.M = T, d_imu.data_ptr(), M
-    sh.tag_step, sh.tag_pose_clean, sh.tag_stamp = d_step.data_ptr(), d_pose.data_ptr(), d_stamp.data_ptr()
-    sh.truth, sh.t_start, sh.on_device = d_truth.data_ptr(), 0.0, 1
-
-    # ---- pinned host inputs (the `e2e` leg) ----
-    h_imu = torch.tensor(scn.imu_clean).pin_memory()
-    h_pose = torch.tensor(scn.tag_pose_clean).pin_memory()
-    h_stamp = torch.tensor(scn.tag_stamp).pin_memory()
-    h_step = torch.tensor(scn.tag_step, dtype=torch.int32).pin_memory()
-    h_truth = torch.tensor(scn.truth).pin_memory()
-    hs = q.QekfSharedStreams()
-    hs.T, hs.imu_clean, hs.M = T, h_imu.data_ptr(), M
-    hs.tag_step, hs.tag_pose_clean, hs.tag_stamp = h_step.data_ptr(), h_pose.data_ptr(), h_stamp.data_ptr()
-    hs.truth, hs.t_start, hs.on_device = h_truth.data_ptr(), 0.0, 0
-    h2d = h_imu.numel() * 8 + h_pose.numel() * 8 + h_stamp.numel() * 8 + h_step.numel() * 4 + h_truth.numel() * 8
-    h_stats = np.zeros((nb, q.STAT_DIM))
-
-    def one_step(shared, host_result):
-        """One pass of the hot path: reset -> fused replay of all T ticks -> statistics (all-reduced at N>1)."""
-        b.reset_filters()
-        b.stats_reset()
-        b.run_monte_carlo_device(shared, noise, 0, T)
-        b.copy_stats_device(stats_dev.data_ptr())
-        all_reduce_stats(stats_dev)                 # NCCL sum over the ranks (no-op at N=1)
-        if host_result:
-            h_stats[:] = stats_dev.cpu().numpy()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(shared, host_result, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            one_step(shared, host_result)
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        if host_result:
-            ms = max(ms, wall * 1e3)          # the host-visible time is what a caller of the C ABI sees
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    if args.scaling == "strong":
+        N = args.filters // world                    # the job's total stays `--filters`
+    main = Leg(q, torch, local, rank, world, N, precision=args.precision, multirate=args.multirate, dynamic=args.dynamic_delay,
+               sweep=args.sweep, no_stats=args.no_stats, no_private_dropout=args.no_private_dropout)
+    b, T, stream = main.b, main.T, main.stream
+    hs, h2d = main.host_inputs()
 
     for _ in range(max(args.warmup, 3)):
-        one_step(sh, False)
+        main.one_step(main.sh, False)
     torch.cuda.synchronize()
     b.step_counts(reset=True)
     l0 = b.launch_count
     sampler = ClockSampler(local)
     sampler.start()
-    # the fused kernel alone (for the roofline): events around the launch only, on its stream
-    k_ms = []
-    ms_total = timed(sh, False, args.steps)
+    ms_total = main.timed(main.sh, False, args.steps, dist)
     launches = b.launch_count - l0
     n_pred, n_corr = b.step_counts(reset=True)
-    for _ in range(2):
-        b.reset_filters(); b.stats_reset()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        b.run_monte_carlo_device(sh, noise, 0, T)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        k_ms.append(e0.elapsed_time(e1))
+    k_ms = main.kernel_ms(2)
     clocks = sampler.stop()
-    one_step(hs, True)                              # warm the host path (staging slab allocation)
-    e2e_ms = timed(hs, True, args.steps)
+    main.one_step(hs, True)                              # warm the host path (staging slab allocation)
+    e2e_steps = min(args.steps, 8)
+    e2e_ms = main.timed(hs, True, e2e_steps, dist)
+
+    # ---- outside the timed regions: parity of this rank's filters against the oracle (max over ranks) ----
+    parity = None
+    if not args.no_parity:
+        parity = main.parity()
+        if dist is not None:
+            t = torch.tensor([parity["state_norm_rel"], parity["cov_norm_rel"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            parity["state_norm_rel"], parity["cov_norm_rel"] = float(t[0].item()), float(t[1].item())
+            parity["ranks_checked"] = world
+            parity["filters_checked"] *= world
+    h_stats = main.h_stats.copy()
+    peak = nat.measure_fma_peak(local, main.prec)
+    p, scn, prec = main.p, main.scn, main.prec
+    main.close()
+
+    # ---- secondary workloads of BASELINE.json (configs 3 FP32, delayed fusion, config 5), same timing method ----
+    legs = None
+    default_main = (args.precision == 64 and not args.multirate and not args.sweep and not args.no_stats
+                    and not args.no_private_dropout)
+    if not args.no_legs and default_main:
+        legs = {}
+        for name, kw in (("fp32", dict(precision=32)),
+                         ("delayed_fusion_fixed", dict(multirate=True)),
+                         ("delayed_fusion_dynamic", dict(multirate=True, dynamic=True)),
+                         ("config5_sweep_delayed_dynamic", dict(multirate=True, dynamic=True, sweep=True))):
+            legs[name] = run_leg(q, torch, nat, local, rank, world, dist, N, args.leg_steps, **kw)
 
     if rank != 0:
         if dist is not None:
@@ -325,16 +453,8 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     steps_per_pass = N * T * world
     value = steps_per_pass / (ms_per_step * 1e-3)
-    e2e_value = steps_per_pass / (e2e_ms / args.steps * 1e-3)
-    # roofline of the dominant kernel (run_kernel): exact executed work / kernel time
-    fp, fc = FLOPS[(int(p.est_bias), int(p.direct_orien_method))]
-    if prec == q.QEKF_FP32:
-        fc += JOSEPH_EXTRA_FLOPS[int(p.est_bias)]      # the FP32 mode's refined gain (Joseph form), DESIGN.md section 7
-    pred_per_launch, corr_per_launch = n_pred / args.steps, n_corr / args.steps
-    flops_per_launch = pred_per_launch * fp + corr_per_launch * fc
-    k_t = float(np.mean(k_ms)) * 1e-3
-    peak = nat.measure_fma_peak(local, prec)
-    achieved = flops_per_launch / k_t / 1e12
+    e2e_value = steps_per_pass / (e2e_ms / e2e_steps * 1e-3)
+    roof = main.roofline(k_ms, n_pred / args.steps, n_corr / args.steps, peak)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -351,26 +471,22 @@ def run_ours(args):
             traffic_src = tj[key]["source"].split(":")[0]
     except Exception:
         pass
+    roof["traffic"], roof["traffic_unit"], roof["traffic_source"] = traffic, "DRAM bytes per launch (ncu)", traffic_src
+    k_t = k_ms * 1e-3
     hbm_bytes = N * STATE_BYTES * (1 if prec == q.QEKF_FP64 else 0.5) + h2d
+    threads = os.cpu_count() or 1
+    sample = cpu_sample_filters(threads)
     line = {
         "metric": "EKF filter-steps/s (propagate+update)", "value": value, "unit": "filter-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64" if prec == q.QEKF_FP64 else "f32", "data": "synthetic",
-        "config": workload_config(args, scn),
+        "config": workload_config(args, scn, sample if world == 1 and not args.no_cpu_baseline else None),
         "e2e": {"value": e2e_value, "unit": "filter-steps/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(h_stats.nbytes)},
+                "d2h_bytes_per_step": int(h_stats.nbytes), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64" if prec == q.QEKF_FP64 else "fp32", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": traffic_src,
-                     "peak_source": "self-measured FMA microbenchmark in this run (qekf_measure_fma_peak); "
-                                    "MEASURED_PEAKS.json has no CUDA-core figure",
-                     "kernel": "run_kernel", "kernel_ms": k_t * 1e3,
-                     "flops_per_filter_step": flops_per_launch / (N * T),
-                     "work": {"prediction_steps": pred_per_launch, "correction_steps": corr_per_launch,
-                              "flops_per_prediction": fp, "flops_per_correction": fc}},
+        "roofline": roof,
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_bytes / k_t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_bytes / k_t / 1e9 / hbm_peak, "traffic": traffic,
                          "algorithmic_bytes": hbm_bytes,
@@ -379,16 +495,31 @@ def run_ours(args):
                   "mean_nees_final": float(h_stats[-1, 15] / max(h_stats[-1, 16], 1)),
                   "samples_final": float(h_stats[-1, 16]), "diverged_total": float(h_stats[:, 18].sum())},
     }
+    if args.scaling == "strong":
+        line["config"]["filters_per_gpu"] = N
+        line["config"]["filters_total"] = N * world
+    if parity is not None:
+        line["parity"] = parity
+    if legs is not None:
+        line["legs"] = legs
+    if dist is not None:
+        line["comm"] = {"backend": "nccl", "nranks": int(dist.get_world_size()),
+                        "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version()),
+                        "collective": "all_reduce(sum, f64) of the [%d][%d] statistics, once per pass" % (h_stats.shape[0], h_stats.shape[1])}
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sample = max(32, 32 * threads)
-        streams = cpu_streams(q, scn, sample)
-        cpu_replay(p, scn, streams, threads)
-        reps = [cpu_replay(p, scn, streams, threads) for _ in range(3)]
+        from oracle import ekf_oracle as orc
+        op = orc.params_from(p)
+        streams = cpu_streams(bench_noise(q), scn, sample)
+        cpu_replay(op, scn, streams, threads)
+        reps = [cpu_replay(op, scn, streams, threads) for _ in range(3)]
         dt = float(np.mean(reps))
+        one = tuple(np.ascontiguousarray(a[..., :32]) for a in streams)
+        dt1 = cpu_replay(op, scn, one, 1)
         line["cpu_baseline"] = {"value": sample * T / dt, "unit": "filter-steps/s", "cores": threads, "kind": "port",
                                 "sample": "%d filters x %d ticks of the same workload, %.1f s per replay; %s"
-                                          % (sample, T, dt, CPU_NOTE)}
+                                          % (sample, T, dt, CPU_NOTE),
+                                "single_thread": {"value": 32 * T / dt1, "unit": "filter-steps/s", "cores": 1,
+                                                  "sample": "32 filters x %d ticks, %.1f s" % (T, dt1)}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -408,6 +539,11 @@ def main():
                     help="BASELINE config 5: per-filter Q / R within x[0.1, 10] of the preset (log-uniform), camera extrinsic "
                          "+-2 cm / +-1 deg (use with --multirate --dynamic-delay)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of three id windows after the timed passes")
+    ap.add_argument("--no-legs", action="store_true", help="skip the secondary workloads (FP32, delayed fusion, config 5)")
+    ap.add_argument("--leg-steps", type=int, default=3)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --filters per GPU (default); strong: --filters in total, split over the ranks")
     ap.add_argument("--no-stats", action="store_true", help="diagnostic: never sample statistics")
     ap.add_argument("--no-private-dropout", action="store_true", help="diagnostic: drop the per-filter dropout window")
     args = ap.parse_args()

@@ -1291,14 +1291,15 @@ __global__ void __launch_bounds__(96 * G, 1) run_kernel_coop(const __grid_consta
     const int lane = (int)(threadIdx.x & 31);
     const int g = warp / 3, c = warp - 3 * g;
     const int f = g * 32 + lane;
-    const int64_t i = (int64_t)blockIdx.x * F + f;
+    const int64_t slot = (int64_t)blockIdx.x * F + f;
+    const bool live = slot < a.st.n;
+    const int64_t i = (live && a.st.perm) ? (int64_t)a.st.perm[slot] : slot;
     if (threadIdx.x < 3) fill_role_consts(a.c, (int)threadIdx.x, rcs + threadIdx.x * RC_N);
     __syncthreads();
     PLane<T, NB, F> P;
     P.setup(sm + f, c);
     const GroupSync gs{ g + 1, nullptr, nullptr, 96 };
     const CtaCtx<T> cta{ g, G, sm + (size_t)Lay<NB>::CB * F };
-    const bool live = i < a.st.n;
     const SPtr<T> rc = SPtr<T>::from(rcs + c * RC_N);
     if constexpr (PF) {
         const ParF<T> par = ParSel<T, true>::make(a.c, a.st, live ? i : 0);

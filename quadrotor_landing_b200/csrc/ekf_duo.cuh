@@ -502,12 +502,14 @@ __global__ void __launch_bounds__(64 * G, 1) run_kernel_duo(const __grid_constan
     const int lane = (int)(threadIdx.x & 31);
     const int g = warp >> 1, role = warp & 1;
     const int f = g * 32 + lane;
-    const int64_t i = (int64_t)blockIdx.x * F + f;
+    const int64_t slot = (int64_t)blockIdx.x * F + f;
+    const bool live = slot < a.st.n;
+    const int64_t i = (live && a.st.perm) ? (int64_t)a.st.perm[slot] : slot;
     PShared<T, N, F> P{ sm + f };
     const XBuf<T, F> X{ sm + (size_t)NP * F + f };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)(NP + X_WORDS) * F);
     const GroupSync gs{ g + 1, nullptr, nullptr, 64 };
-    run_filter_duo<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, X, role, i < a.st.n, gs, vbuf);
+    run_filter_duo<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, X, role, live, gs, vbuf);
 }
 template <int N> constexpr size_t duo_smem_bytes(int groups, size_t tsize)
 {

@@ -50,6 +50,11 @@ template <typename T> struct DeviceState {
     // Per-filter parameter overrides (BASELINE config 5); nullptr = launch-wide constants only.
     const T *pf;              // [PF_DIM][ld]
     const double *pf_delay;   // [2][ld]
+    // Monte-Carlo launches: which filter the thread slot j of the fused replay advances (nullptr = filter j).  The
+    // host orders filters by the start of their private tag dropout, so that the filters sharing a CTA lose and
+    // regain their measurements together and their correction cadence stays aligned; filters are independent and
+    // the noise is keyed by the filter id, so the order changes no result.
+    const int32_t *perm;
 };
 
 // the parameter view of filter i: launch-wide constants, or this filter's column of the override table
@@ -197,7 +202,11 @@ QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nom
     // below would otherwise force the compiler to reload these fields (it cannot rule out aliasing)
     const StatsView sv = a.stats;
     const int64_t ld = a.st.ld;
+#ifdef __CUDA_ARCH__
+    T *const __restrict__ gp = sv.save ? static_cast<T *>(sv.save) + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) : a.st.P + i;
+#else
     T *const __restrict__ gp = a.st.P + i;
+#endif
     int32_t bin = (int32_t)((k + 1) / sv.stride - 1);
     if (bin < 0 || bin >= sv.n_bins) valid = false;
     double sum[STAT_DIM];
@@ -446,7 +455,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         in.raw_imu(k, un);             // software prefetch: un always holds the raw sample of tick k
     }
 
-    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0;
+    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0, n_cev = 0;
     int32_t m = a.m0;
     int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     int32_t pend_m = -1;               // index of the latched arrival; -1 = latched pose lives in st.pend
@@ -508,6 +517,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
             held = 0;
         }
 
+#if defined(__CUDA_ARCH__) && defined(QEKF_DIAG_EVENTS)
+        if (__ballot_sync(0xffffffffu, perform) != 0u) ++n_cev;    // diagnostics: iterations in which this warp runs the correction
+#endif
         if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
             // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
             T u[6];
@@ -557,7 +569,10 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 #ifdef __CUDA_ARCH__
         atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
         atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
-        if ((i & 31) == 0) atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);   // loop iterations per warp
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);   // loop iterations per warp
+            atomicAdd(a.st.counts + 3, (unsigned long long)n_cev);    // ... of which the warp ran the correction
+        }
         atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
 #else
         a.st.counts[0] += n_pred;
@@ -875,15 +890,17 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     constexpr int N = BIAS ? 15 : 9;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
-    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = slot < a.st.n;
+    const int64_t i = (live && a.st.perm) ? (int64_t)a.st.perm[slot] : slot;
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
     // padding lanes still take part in the votes
     if (MR) {
         // the sequencer's integers live in the shared memory behind the vote words
-        run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, i < a.st.n, vbuf);
+        run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, live, vbuf);
     } else {
-        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, i < a.st.n, vbuf);
+        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, live, vbuf);
     }
 }
 

@@ -81,6 +81,14 @@ struct qekf_handle {
     size_t d_shared_bytes = 0;
     uint8_t *d_mask = nullptr;       // detection front-end visibility mask [M]
     size_t d_mask_bytes = 0;
+    // slot -> filter order of the Monte-Carlo replay (filters sorted by the start of their private dropout), and the
+    // noise-spec fields it was derived from
+    int32_t *d_perm = nullptr;
+    void *stats_save = nullptr;      // [np][ld]: slot-indexed parking space of the statistics sample while d_perm is in use
+    uint64_t perm_seed = 0;
+    int64_t perm_gid0 = 0;
+    int32_t perm_len = 0, perm_lo = 0, perm_hi = 0;
+    bool perm_on = true;             // QEKF_NO_PERM=1 disables it (A/B runs)
     // launch bookkeeping
     int64_t launches = 0;
     // mapping of the fused replay (qekf_set_mapping), where the kernels exist (FP64, single-rate): 2 = two role-specialised
@@ -101,6 +109,7 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     s.ring_len = h->ring_len; s.dmax_m1 = h->dmax - 1;
     s.pf = h->pf_on ? (const T *)h->pf : nullptr;
     s.pf_delay = h->pf_on ? h->pf_delay : nullptr;
+    s.perm = nullptr;
     return s;
 }
 
@@ -136,7 +145,8 @@ int free_state(qekf_handle *h)
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
     cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared); cudaFree(h->counts);
     cudaFree(h->xc); cudaFree(h->Pc); cudaFree(h->ring); cudaFree(h->nh); cudaFree(h->hpos); cudaFree(h->hlen);
-    cudaFree(h->pf); cudaFree(h->pf_delay); cudaFree(h->d_mask);
+    cudaFree(h->pf); cudaFree(h->pf_delay); cudaFree(h->d_mask); cudaFree(h->d_perm); cudaFree(h->stats_save);
+    h->d_perm = nullptr; h->perm_len = 0; h->stats_save = nullptr;
     h->d_mask = nullptr; h->d_mask_bytes = 0;
     h->xc = h->Pc = h->ring = nullptr; h->nh = h->hpos = h->hlen = nullptr; h->ring_len = 0;
     h->pf = nullptr; h->pf_delay = nullptr; h->pf_on = false;
@@ -262,7 +272,10 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
     a.k0 = k0; a.n_steps = n_steps; a.m0 = m0;
     if (ns) {
         a.ns = *ns;
+        // slot order (qekf_run_monte_carlo keeps it in step with the noise spec; may be null); thread-per-filter kernels only
+        a.st.perm = (h->lanes_per_filter == 1 || h->precision != QEKF_FP64 || h->p.multirate_ekf) ? h->d_perm : nullptr;
         if (h->stats_acc && truth && h->stats_stride > 0) {
+            a.stats.save = a.st.perm ? h->stats_save : nullptr;
             a.stats.acc = h->stats_acc; a.stats.truth = truth;
             a.stats.n_bins = h->stats_bins; a.stats.stride = h->stats_stride;
             // two-sided 95% chi-square interval for n degrees of freedom
@@ -354,6 +367,41 @@ int store_rows(qekf_handle *h, void *dev, int rows, int64_t first, int64_t count
 bool range_ok(const qekf_handle *h, int64_t first, int64_t count)
 {
     return h && first >= 0 && count >= 0 && first + count <= h->n;
+}
+
+// Slot order of the Monte-Carlo replay: filters sorted (counting sort, stable) by the first tick of their private
+// dropout window, a pure function of (seed, global id).  Rebuilt only when the fields it depends on change.
+int ensure_perm(qekf_handle *h, const NoiseSpec &ns)
+{
+    const bool wanted = h->perm_on && ns.rdrop_len > 0 && ns.rdrop_hi > ns.rdrop_lo && h->n > 1;
+    if (!wanted) {
+        if (h->d_perm) { CUDA_TRY(cudaStreamSynchronize(h->stream)); cudaFree(h->d_perm); h->d_perm = nullptr; h->perm_len = 0; }
+        return QEKF_OK;
+    }
+    if (h->d_perm && h->perm_seed == ns.seed && h->perm_gid0 == ns.gid0 && h->perm_len == ns.rdrop_len &&
+        h->perm_lo == ns.rdrop_lo && h->perm_hi == ns.rdrop_hi)
+        return QEKF_OK;
+    const int64_t n = h->n;
+    const int32_t span = ns.rdrop_hi - ns.rdrop_lo;
+    std::vector<int32_t> start((size_t)n), perm((size_t)n);
+    std::vector<int64_t> head((size_t)span + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        start[(size_t)i] = private_dropout_start(ns, ns.gid0 + i) - ns.rdrop_lo;
+        head[(size_t)start[(size_t)i] + 1]++;
+    }
+    for (int32_t b = 0; b < span; ++b) head[(size_t)b + 1] += head[(size_t)b];
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)head[(size_t)start[(size_t)i]]++] = (int32_t)i;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->d_perm) CUDA_TRY(cudaMalloc(&h->d_perm, (size_t)n * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(h->d_perm, perm.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->perm_seed = ns.seed; h->perm_gid0 = ns.gid0; h->perm_len = ns.rdrop_len; h->perm_lo = ns.rdrop_lo; h->perm_hi = ns.rdrop_hi;
+    return QEKF_OK;
+}
+int ensure_stats_save(qekf_handle *h)
+{
+    if (h->d_perm && h->stats_acc && !h->stats_save)
+        CUDA_TRY(cudaMalloc(&h->stats_save, (size_t)h->np * (size_t)h->ld * h->tsize));
+    return QEKF_OK;
 }
 
 int ensure_in(qekf_handle *h, size_t bytes)
@@ -491,6 +539,8 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
         if (e && atoi(e) >= 1 && atoi(e) <= 3) h->lanes_per_filter = atoi(e);
         e = getenv("QEKF_COOP_GROUPS");
         if (e && coop_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->coop_groups = atoi(e);
+        e = getenv("QEKF_NO_PERM");
+        if (e && atoi(e) != 0) h->perm_on = false;
         e = getenv("QEKF_DUO_GROUPS");
         if (e && duo_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->duo_groups = atoi(e);
     }
@@ -1025,6 +1075,10 @@ int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qek
     for (size_t m = 0; m < steps.size(); ++m)
         if (steps[m] < k0) m0 = (int32_t)(m + 1);
     NoiseSpec ns = to_device_noise(*n);
+    rc = ensure_perm(h, ns);
+    if (rc) return rc;
+    rc = ensure_stats_save(h);
+    if (rc) return rc;
     return run_dispatch(h, in, k0, n_steps, m0, &ns, truth);
 }
 
@@ -1141,7 +1195,7 @@ int qekf_step_counts(qekf_handle *h, int64_t *n_predict, int64_t *n_correct, int
     CUDA_TRY(cudaMemcpy(c, h->counts, sizeof c, cudaMemcpyDeviceToHost));
     *n_predict = (int64_t)c[0]; *n_correct = (int64_t)c[1];
     if (getenv("QEKF_DIAG"))
-        fprintf(stderr, "[qekf diag] predicts %llu corrects %llu | warp iterations %llu | stat samples %llu\n", c[0], c[1], c[2], c[4]);
+        fprintf(stderr, "[qekf diag] predicts %llu corrects %llu | warp iterations %llu, with a correction %llu | stat samples %llu\n", c[0], c[1], c[2], c[3], c[4]);
     if (reset) CUDA_TRY(cudaMemset(h->counts, 0, sizeof c));
     return QEKF_OK;
 }

@@ -25,6 +25,8 @@ scn = scenario.generate(p, sp)
 noise = bench.bench_noise(q)
 if "nodrop" in args:
     noise.rand_dropout_len = 0
+if "droplate" in args:          # private dropouts exist, but none starts before tick 5000
+    noise.rand_dropout_lo = 5000
 if "nocommon" in args:
     noise.dropout_k0 = noise.dropout_k1 = 0
 b = q.BatchEKF(p, N, precision=prec)
