@@ -44,6 +44,7 @@ template <typename T> __global__ void reset_kernel(DeviceState<T> st, Consts<T> 
     if (reset_nominal) {
         st.x[9 * st.ld + i] = T(1);
         st.aux[9 * st.ld + i] = T(1);
+        st.pend[6 * st.ld + i] = 1.0;      // apriltag_orien = identity (cpp:14): a forced initialize_state before any tag
     }
     int e = 0;
     for (int a = 0; a < nstates; ++a)

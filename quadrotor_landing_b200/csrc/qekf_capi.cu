@@ -62,6 +62,7 @@ struct qekf_handle {
     int ring_len = 0, dmax = 1;
     // per-filter parameter overrides: host copies [dim][N] per field, derived device tables
     std::vector<double> pf_host[5];
+    bool pf_overridden[5] = { false, false, false, false, false };   // which fields the caller has set (the others follow p)
     bool pf_on = false;
     void *pf = nullptr;
     double *pf_delay = nullptr;
@@ -272,8 +273,11 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
     a.k0 = k0; a.n_steps = n_steps; a.m0 = m0;
     if (ns) {
         a.ns = *ns;
-        // slot order (qekf_run_monte_carlo keeps it in step with the noise spec; may be null); thread-per-filter kernels only
-        a.st.perm = (h->lanes_per_filter == 1 || h->precision != QEKF_FP64 || h->p.multirate_ekf) ? h->d_perm : nullptr;
+        // slot order (qekf_run_monte_carlo keeps it in step with the noise spec; may be null).  Single-rate thread-per-filter
+        // kernels only: the delayed-fusion kernel touches its per-filter IMU ring in HBM every tick, and a permuted
+        // filter index makes those accesses uncoalesced (measured: 3.5e9 -> 1.6e9 filter-steps/s)
+        const bool tpf = h->lanes_per_filter == 1 || h->precision != QEKF_FP64;
+        a.st.perm = (tpf && !h->p.multirate_ekf) ? h->d_perm : nullptr;
         if (h->stats_acc && truth && h->stats_stride > 0) {
             a.stats.save = a.st.perm ? h->stats_save : nullptr;
             a.stats.acc = h->stats_acc; a.stats.truth = truth;
@@ -573,6 +577,13 @@ int qekf_set_params(qekf_handle *h, const qekf_params *p)
     if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
     int rc = check_params(p);
     if (rc) return rc;
+    if (h->pf_on && h->pf_overridden[QEKF_PF_DELAY]) {
+        // the per-filter delays stay in force: they must still fit the ring with the new update rate
+        const std::vector<double> &v = h->pf_host[QEKF_PF_DELAY];
+        for (size_t i = 0; i < (size_t)h->n; ++i)
+            if (step_of_delay(v[i], p->update_freq) > 4096)
+                return fail(QEKF_ERR_BAD_ARG, "a per-filter measurement_delay spans more than 4096 ticks at the new update_freq");
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     const bool shape_change = (p->est_bias != 0) != (h->p.est_bias != 0);
     h->p = *p;
@@ -585,7 +596,13 @@ int qekf_set_params(qekf_handle *h, const qekf_params *p)
     }
     rc = reset_cov(h, false);     // initialize_params: cov_pert = cov_init (cpp:114)
     if (rc) return rc;
-    if (h->pf_on) { rc = rebuild_pf(h); if (rc) return rc; }
+    if (h->pf_on) {
+        // fields never overridden follow the handle-wide value (include/qekf.h): re-seed them from the new parameters
+        for (int f = 0; f < 5; ++f)
+            if (!h->pf_overridden[f]) seed_pf_field(h, f);
+        rc = rebuild_pf(h);
+        if (rc) return rc;
+    }
     if (!h->p.multirate_ekf) return QEKF_OK;
     // Delayed fusion: the history restarts from the current head.  (The reference keeps its old history
     // vectors here, so its next delayed correction would silently discard the covariance reset.)
@@ -601,39 +618,76 @@ int qekf_get_params(const qekf_handle *h, qekf_params *p)
     return QEKF_OK;
 }
 
+// (re)seed the host copy of per-filter field `f` from the handle-wide parameters
+static void seed_pf_field(qekf_handle *h, int f)
+{
+    static const int dims[5] = { 12, 6, 3, 4, 2 };
+    const size_t N = (size_t)h->n;
+    const qekf_params &p = h->p;
+    std::vector<double> &v = h->pf_host[f];
+    v.assign((size_t)dims[f] * N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+        if (f == QEKF_PF_Q) {
+            for (int k = 0; k < 3; ++k) {
+                v[(0 + k) * N + i] = p.Q_a[k]; v[(3 + k) * N + i] = p.Q_w[k];
+                v[(6 + k) * N + i] = p.Q_ab[k]; v[(9 + k) * N + i] = p.Q_wb[k];
+            }
+        } else if (f == QEKF_PF_R) {
+            for (int k = 0; k < 3; ++k) { v[(0 + k) * N + i] = p.R_r[k]; v[(3 + k) * N + i] = p.R_ang[k]; }
+        } else if (f == QEKF_PF_R_V_CV) {
+            for (int k = 0; k < 3; ++k) v[k * N + i] = p.r_v_cv[k];
+        } else if (f == QEKF_PF_Q_VC) {
+            for (int k = 0; k < 4; ++k) v[k * N + i] = p.q_vc[k];
+        } else {
+            v[0 * N + i] = p.measurement_delay;
+            v[1 * N + i] = p.dyn_measurement_delay_offset;
+        }
+    }
+}
+
 int qekf_set_filter_params(qekf_handle *h, int field, const double *values)
 {
     static const int dims[5] = { 12, 6, 3, 4, 2 };
     if (!h || !values) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     if (field < 0 || field > QEKF_PF_DELAY) return fail(QEKF_ERR_BAD_ARG, "unknown per-filter field");
-    CUDA_TRY(cudaSetDevice(h->device));
     const size_t N = (size_t)h->n;
-    if (!h->pf_on) {
-        // first override: every field starts from the handle-wide parameters
-        const qekf_params &p = h->p;
-        for (int f = 0; f < 5; ++f) h->pf_host[f].assign((size_t)dims[f] * N, 0.0);
-        for (size_t i = 0; i < N; ++i) {
-            for (int k = 0; k < 3; ++k) {
-                h->pf_host[QEKF_PF_Q][(0 + k) * N + i] = p.Q_a[k]; h->pf_host[QEKF_PF_Q][(3 + k) * N + i] = p.Q_w[k];
-                h->pf_host[QEKF_PF_Q][(6 + k) * N + i] = p.Q_ab[k]; h->pf_host[QEKF_PF_Q][(9 + k) * N + i] = p.Q_wb[k];
-                h->pf_host[QEKF_PF_R][(0 + k) * N + i] = p.R_r[k]; h->pf_host[QEKF_PF_R][(3 + k) * N + i] = p.R_ang[k];
-                h->pf_host[QEKF_PF_R_V_CV][k * N + i] = p.r_v_cv[k];
-            }
-            for (int k = 0; k < 4; ++k) h->pf_host[QEKF_PF_Q_VC][k * N + i] = p.q_vc[k];
-            h->pf_host[QEKF_PF_DELAY][0 * N + i] = p.measurement_delay;
-            h->pf_host[QEKF_PF_DELAY][1 * N + i] = p.dyn_measurement_delay_offset;
-        }
-        CUDA_TRY(cudaMalloc(&h->pf, (size_t)PF_DIM * (size_t)h->ld * h->tsize));
-        CUDA_TRY(cudaMalloc(&h->pf_delay, 2 * (size_t)h->ld * sizeof(double)));
-        h->pf_on = true;
-    }
+    // validate before anything is allocated or enabled: a rejected call leaves the handle as it was
     if (field == QEKF_PF_DELAY)
         for (size_t i = 0; i < N; ++i)
             if (!(values[i] >= 0) || step_of_delay(values[i], h->p.update_freq) > 4096)
                 return fail(QEKF_ERR_BAD_ARG, "per-filter measurement_delay out of range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const bool first = !h->pf_on;
+    if (first) {
+        // first override: every field starts from the handle-wide parameters
+        for (int f = 0; f < 5; ++f) { seed_pf_field(h, f); h->pf_overridden[f] = false; }
+        if (cudaMalloc(&h->pf, (size_t)PF_DIM * (size_t)h->ld * h->tsize) != cudaSuccess ||
+            cudaMalloc(&h->pf_delay, 2 * (size_t)h->ld * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(h->pf); cudaFree(h->pf_delay);
+            h->pf = nullptr; h->pf_delay = nullptr;
+            for (auto &v : h->pf_host) v.clear();
+            return fail(QEKF_ERR_CUDA, "out of device memory for the per-filter parameter tables");
+        }
+    }
+    std::vector<double> previous;
+    if (!first) previous = h->pf_host[field];
     std::memcpy(h->pf_host[field].data(), values, (size_t)dims[field] * N * sizeof(double));
     int rc = rebuild_pf(h);
-    if (rc) return rc;
+    if (rc) {
+        // the device tables are not trustworthy: first call -> overrides stay off; later call -> previous values back
+        if (first) {
+            cudaFree(h->pf); cudaFree(h->pf_delay);
+            h->pf = nullptr; h->pf_delay = nullptr;
+            for (auto &v : h->pf_host) v.clear();
+        } else {
+            h->pf_host[field] = previous;
+            rebuild_pf(h);
+        }
+        return rc;
+    }
+    h->pf_on = true;                 // only now do the replay kernels read the tables
+    h->pf_overridden[field] = true;
     if (field == QEKF_PF_DELAY && h->p.multirate_ekf) {
         const int old_len = h->ring_len;
         rc = alloc_history(h);

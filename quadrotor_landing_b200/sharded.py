@@ -38,8 +38,9 @@ class ShardedMonteCarlo:
     so that the sharding and reduction logic runs under gloo without a GPU.
     """
 
-    def __init__(self, make_batch, n_total: int, rank: int, world: int, noise, n_bins: int, stride: int):
+    def __init__(self, make_batch, n_total: int, rank: int, world: int, noise, n_bins: int, stride: int, empty_device=None):
         self.rank, self.world, self.n_total = rank, world, n_total
+        self.empty_device = empty_device     # where an empty shard's zero statistics live (default: by backend)
         self.first, self.count = shard_range(n_total, rank, world)
         self.noise = copy.copy(noise)
         self.noise.first_global_id = noise.first_global_id + self.first
@@ -55,6 +56,13 @@ class ShardedMonteCarlo:
             self.batch.run_monte_carlo(scn, self.noise, k0, n_steps)
             stats = self.batch.stats_tensor()
         else:
+            # an empty shard (more ranks than filters) still takes part in the collective, with zeros on the device the
+            # backend reduces on: NCCL needs a CUDA tensor on this rank's GPU, gloo a CPU one
+            import torch.distributed as dist
             from ._native import STAT_DIM
-            stats = torch.zeros((self.n_bins, STAT_DIM), dtype=torch.float64)
+            device = self.empty_device
+            if device is None:
+                on_nccl = dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+                device = torch.device("cuda", torch.cuda.current_device()) if on_nccl else torch.device("cpu")
+            stats = torch.zeros((self.n_bins, STAT_DIM), dtype=torch.float64, device=device)
         return all_reduce_stats(stats, group)

@@ -113,3 +113,14 @@ def test_two_ranks_reproduce_the_single_rank_job(tmp_path):
     assert np.array_equal(parts[0]["stats"][:, 16:19], ref[:, 16:19])          # sample / hit / divergence counts
     assert np.max(np.abs(parts[0]["stats"] - ref)) <= 1e-12 * np.max(np.abs(ref))
     assert ref[-1, 16] == n_total
+
+
+def test_empty_shard_takes_part_in_the_reduction(tmp_path):
+    """More ranks than filters: the rank that owns nothing contributes zeros (on the backend's device) and every rank
+    still ends with the job-wide statistics."""
+    n_total, world = 1, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert [int(pp["count"]) for pp in parts] == [1, 0]
+    assert np.array_equal(parts[0]["stats"], parts[1]["stats"]) and parts[1]["stats"][-1, 16] == 1
