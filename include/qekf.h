@@ -145,6 +145,22 @@ int qekf_initialize_state(qekf_handle *h, int reinit_bias);
  * vectors of the reference are kept as a lagged checkpoint plus a ring of IMU inputs and re-evaluated on demand;
  * what the accessors return after the call is what the reference's members would hold. */
 int qekf_filter_update(qekf_handle *h, double t_curr);
+/* Latch a tag pose WITHOUT raising measurement_ready and without the first-detection initialisation: what
+ * RelativePoseEKF::initialize_state needs when the caller re-initialises by hand (it reads the latched apriltag_pos /
+ * apriltag_orien members and never touches measurement_ready, relative_pose_EKF.cpp:305-344). */
+int qekf_latch_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp);
+/* One timer tick of the node in ONE launch (relative_pose_EKF_node.cpp:144-283): the tag callback if a detection
+ * arrived since the last tick (tag_mode 1 = AprilTagSubCallback: latch + measurement_ready + first-detection
+ * initialisation; 2 = latch only; 0 = none), the IMU sample, filter_update(t_curr), and the members the node reads
+ * afterwards for the first n_out filters, QEKF_TICK_RECORD doubles each:
+ *   x[16] | cov_pert[n*n] row-major (n = qekf_num_states) padded to 225 | aux[11] |
+ *   state_initialized measurement_ready performed_correction filter_active upds_since_correction x_hist.size()
+ * Inputs and records travel through mapped pinned memory: the host pays one launch and one stream synchronisation.
+ * Same arithmetic and sequencing as qekf_set_tag + qekf_set_imu + qekf_filter_update + the getters.  Handles without
+ * per-filter overrides. */
+#define QEKF_TICK_RECORD 258
+int qekf_tick(qekf_handle *h, const double accel[3], const double gyro[3], int tag_mode, const double tag_pos[3],
+              const double tag_quat_xyzw[4], double tag_stamp, double t_curr, int n_out, double *records);
 
 /* ---- batch replay: filter_update iterated n_steps times inside one kernel launch -------------- */
 

@@ -14,6 +14,7 @@
 #ifndef RELATIVE_POSE_EKF_GPU_HPP
 #define RELATIVE_POSE_EKF_GPU_HPP
 
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -116,20 +117,30 @@ public:
         refresh();
     }
     // Initialize state to last received AprilTag relative pose                  (cpp:305-344)
+    // (reads the latched apriltag_pos / apriltag_orien members; measurement_ready is not its business)
     void initialize_state(bool reinit_bias)
     {
-        push_tag();
+        const bool ready = measurement_ready;
+        const double q[4] = { apriltag_orien.x(), apriltag_orien.y(), apriltag_orien.z(), apriltag_orien.w() };
+        ok(qekf_latch_tag(h_, apriltag_pos.data(), q, apriltag_time));
         ok(qekf_initialize_state(h_, reinit_bias ? 1 : 0));
         refresh();
+        measurement_ready = ready;
     }
     // Perform periodic EKF filter update                                        (cpp:127-303)
+    // One launch: the tag callback's effect (if a detection is waiting), the IMU sample, the tick, and every member the
+    // node reads afterwards in one record (qekf_tick).
     void filter_update(double t_curr)
     {
-        if (measurement_ready) push_tag();
-        ok(qekf_set_imu(h_, IMU_accel.data(), IMU_ang_vel.data()));
-        ok(qekf_filter_update(h_, t_curr));
-        refresh();
+        const auto t0 = std::chrono::steady_clock::now();
+        double rec[QEKF_TICK_RECORD];
+        const double q[4] = { apriltag_orien.x(), apriltag_orien.y(), apriltag_orien.z(), apriltag_orien.w() };
+        ok(qekf_tick(h_, IMU_accel.data(), IMU_ang_vel.data(), measurement_ready ? 1 : 0, apriltag_pos.data(), q,
+                     apriltag_time, t_curr, 1, rec));
+        unpack(rec, rec + 16, rec + 16 + 225, rec + 16 + 225 + 11);
+        last_tick_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
+    double last_tick_seconds = 0;      // host time of the last filter_update() call (launch + synchronisation + unpack)
 
     // ---- members, named as in relative_pose_EKF.hpp:32-133 ----
     std::mutex mtx_IMU, mtx_apriltag, mtx_state;
@@ -231,24 +242,24 @@ private:
         p.multirate_ekf = multirate_ekf; p.dynamic_meas_delay = dynamic_meas_delay;
         return p;
     }
-    // AprilTagSubCallback's effect on the estimator (node.cpp:158-174): latch pose + stamp, raise
-    // measurement_ready, initialise on the first detection.
-    void push_tag()
-    {
-        const double q[4] = { apriltag_orien.x(), apriltag_orien.y(), apriltag_orien.z(), apriltag_orien.w() };
-        ok(qekf_set_tag(h_, apriltag_pos.data(), q, apriltag_time));
-    }
-    // copy what the node reads after a tick (node.cpp:184-281) out of the device
+    // copy what the node reads after a tick (node.cpp:184-281) out of the device (set-up paths; a tick gets the same
+    // values in its record)
     void refresh()
     {
-        double x[16], aux[11];
-        int32_t fl[6];
+        double x[16], aux[11], fl[6];
+        int32_t fi[6];
         const int n = qekf_num_states(h_);
         std::vector<double> P((size_t)n * (size_t)n);
         ok(qekf_get_state(h_, 0, 1, x));
         ok(qekf_get_cov(h_, 0, 1, P.data()));
         ok(qekf_get_aux(h_, 0, 1, aux));
-        ok(qekf_get_flags(h_, 0, 1, fl));
+        ok(qekf_get_flags(h_, 0, 1, fi));
+        for (int i = 0; i < 6; ++i) fl[i] = fi[i];
+        unpack(x, P.data(), aux, fl);
+    }
+    void unpack(const double *x, const double *P, const double *aux, const double *fl)
+    {
+        const int n = qekf_num_states(h_);
         for (int i = 0; i < 3; ++i) {
             r_nom(i) = x[i]; v_nom(i) = x[3 + i]; ab_nom(i) = x[10 + i]; wb_nom(i) = x[13 + i];
             accel_rel(i) = aux[i]; r_t_vt_obs(i) = aux[3 + i];
@@ -257,10 +268,10 @@ private:
         q_tv_obs = Quat(aux + 6);
         measurement_delay_curr = aux[10];
         if (cov_pert.rows() != n) cov_pert.resize(n, n);
-        cov_pert.d = P;
+        cov_pert.d.assign(P, P + (size_t)n * (size_t)n);
         num_states = n;
         state_initialized = fl[0] != 0; measurement_ready = fl[1] != 0; performed_correction = fl[2] != 0;
-        filter_active = fl[3] != 0; upds_since_correction = fl[4]; history_length = fl[5];
+        filter_active = fl[3] != 0; upds_since_correction = (int)fl[4]; history_length = (int)fl[5];
     }
 
     qekf_handle *h_ = nullptr;

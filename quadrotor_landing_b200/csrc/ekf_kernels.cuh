@@ -917,24 +917,20 @@ QEKF_FN void rebase_history(const DeviceState<T> &st, int64_t i, const Nominal<T
     st.hlen[i] = 1;
 }
 
-// AprilTagSubCallback with one pose shared by all filters (node.cpp:153-176)
-template <typename T, bool BIAS, bool PF, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) deliver_tag_kernel(DeviceState<T> st, Consts<T> c, const double *pose8,
-                                                            int force_init, int reinit_bias)
+// AprilTagSubCallback for filter i with pose8 = (position, orientation xyzw, stamp)  (node.cpp:153-176):
+// latch the pose, raise measurement_ready (unless raise_ready = 0: the latch only, what a forced initialize_state
+// of the facade needs), initialise on the first detection; force_init: initialize_state from the latched members.
+template <typename T, bool BIAS, bool PF, class PS>
+QEKF_FN void deliver_one(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init, int reinit_bias,
+                         int raise_ready, PS &P, int64_t i)
 {
-    constexpr int N = BIAS ? 15 : 9;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
-    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= st.n) return;
     int32_t flags = st.flags[i];
     if (!force_init) {
 #pragma unroll
         for (int cc = 0; cc < PEND_DIM; ++cc) st.pend[cc * st.ld + i] = pose8[cc];
-        flags |= FLAG_READY;
+        if (raise_ready) flags |= FLAG_READY;
     }
-    if (force_init || !(flags & FLAG_INIT)) {
-        PShared<T, N, BLOCK> P{ sm + threadIdx.x };
+    if (force_init || (raise_ready && !(flags & FLAG_INIT))) {
         Nominal<T> s;
         load_filter<T>(st, i, s, P);
         T tag[7];
@@ -948,6 +944,57 @@ __global__ void __launch_bounds__(BLOCK) deliver_tag_kernel(DeviceState<T> st, C
         flags |= FLAG_INIT;
     }
     st.flags[i] = flags;
+}
+
+// AprilTagSubCallback with one pose shared by all filters (node.cpp:153-176)
+template <typename T, bool BIAS, bool PF, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) deliver_tag_kernel(DeviceState<T> st, Consts<T> c, const double *pose8,
+                                                            int force_init, int reinit_bias, int raise_ready)
+{
+    constexpr int N = BIAS ? 15 : 9;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= st.n) return;
+    PShared<T, N, BLOCK> P{ sm + threadIdx.x };
+    deliver_one<T, BIAS, PF>(st, c, pose8, force_init, reinit_bias, raise_ready, P, i);
+}
+
+// One timer tick of the node for a small batch (the N = 1 drop-in): the tag callback (if a detection arrived since
+// the last tick), filter_update, and the members the node reads afterwards -- one launch of 32-thread CTAs.  Inputs
+// (a.in.imu, pose8) and the output record live in mapped pinned host memory, so a tick costs the host one launch and
+// one stream synchronisation.  Record of filter j, TICK_REC doubles at out + j*TICK_REC:
+//   x[16] | cov_pert[n*n] row-major | aux[11] | state_initialized measurement_ready performed_correction
+//   filter_active upds_since_correction x_hist.size()
+constexpr int TICK_REC = 16 + 225 + AUX_DIM + 6;
+constexpr int TICK_BLOCK = 32;
+template <typename T, bool BIAS, bool DIRECT, bool MR>
+__global__ void __launch_bounds__(TICK_BLOCK) tick_kernel(const __grid_constant__ RunArgs<T> a, const double *pose8,
+                                                          int tag_mode, double *out, int n_out)
+{
+    constexpr int N = BIAS ? 15 : 9;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const int64_t i = (int64_t)blockIdx.x * TICK_BLOCK + threadIdx.x;
+    const bool live = i < a.st.n;
+    PShared<T, N, TICK_BLOCK> P{ sm + threadIdx.x };
+    int *vbuf = reinterpret_cast<int *>(sm + (size_t)TICK_BLOCK * (N * (N + 1) / 2));
+    if (live && tag_mode != 0) deliver_one<T, BIAS, false>(a.st, a.c, pose8, 0, 0, tag_mode == 1, P, i);
+    if (MR) run_filter_mr<T, BIAS, DIRECT, false, false>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, TICK_BLOCK, live, vbuf);
+    else run_filter<T, BIAS, DIRECT, false, false>(a, i, P, live, vbuf);
+    if (live && i < n_out) {
+        const DeviceState<T> &st = a.st;
+        double *r = out + i * TICK_REC;
+        for (int e = 0; e < 16; ++e) r[e] = (double)st.x[e * st.ld + i];
+        for (int p = 0; p < N; ++p)
+            for (int q2 = 0; q2 < N; ++q2) r[16 + p * N + q2] = (double)st.P[sym_idx<N>(p, q2) * st.ld + i];
+        for (int e = 0; e < AUX_DIM; ++e) r[16 + 225 + e] = (double)st.aux[e * st.ld + i];
+        const int32_t f = st.flags[i];
+        double *fl = r + 16 + 225 + AUX_DIM;
+        fl[0] = (f & FLAG_INIT) ? 1 : 0; fl[1] = (f & FLAG_READY) ? 1 : 0; fl[2] = (f & FLAG_CORRECTED) ? 1 : 0;
+        fl[3] = (f & FLAG_ACTIVE) ? 1 : 0; fl[4] = st.upds[i];
+        fl[5] = (f & FLAG_INIT) ? (st.hlen ? st.hlen[i] : 1) : 0;
+    }
 }
 
 // prediction_step applied once to every filter with per-filter inputs u [6][ld] (cpp:346-415)

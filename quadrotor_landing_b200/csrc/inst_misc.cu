@@ -5,12 +5,12 @@ namespace qekf {
 
 template <typename T, bool BIAS, bool PF>
 cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
-                           int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream)
+                           int reinit_bias, int raise_ready, unsigned grid, size_t smem, cudaStream_t stream)
 {
     auto kern = deliver_tag_kernel<T, BIAS, PF, BlockOf<T>::value>;
     cudaError_t e = prep_kernel(kern, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, BlockOf<T>::value, smem, stream>>>(st, c, pose8, force_init, reinit_bias);
+    kern<<<grid, BlockOf<T>::value, smem, stream>>>(st, c, pose8, force_init, reinit_bias, raise_ready);
     return cudaGetLastError();
 }
 
@@ -126,7 +126,7 @@ template cudaError_t launch_fma_peak<float>(float *, int, unsigned, unsigned, cu
 
 #define INST_TB(T, B, F)                                                                                                \
     template cudaError_t launch_deliver<T, B, F>(const DeviceState<T> &, const Consts<T> &, const double *, int, int,   \
-                                                 unsigned, size_t, cudaStream_t);                                      \
+                                                 int, unsigned, size_t, cudaStream_t);                                      \
     template cudaError_t launch_predict<T, B, F>(const DeviceState<T> &, const Consts<T> &, const double *, unsigned,   \
                                                  size_t, cudaStream_t);                                                \
     template cudaError_t launch_correct<T, B, true, F>(const DeviceState<T> &, const Consts<T> &, const double *,       \

@@ -15,6 +15,28 @@ cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStre
     return cudaGetLastError();
 }
 
+template <typename T, bool BIAS, bool DIRECT, bool MR>
+cudaError_t launch_tick(const RunArgs<T> &a, const double *pose8, int tag_mode, double *out, int n_out, cudaStream_t stream)
+{
+    constexpr int N = BIAS ? 15 : 9;
+    auto kern = tick_kernel<T, BIAS, DIRECT, MR>;
+    const size_t smem = (size_t)TICK_BLOCK * (N * (N + 1) / 2) * sizeof(T) + VOTE_WORDS * sizeof(int) +
+                        (MR ? (size_t)TICK_BLOCK * MR_SCRATCH_INTS * sizeof(int32_t) : 0);
+    static unsigned prepared = 0;          // per instantiation and device: the attribute call is not free on a 200 Hz path
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(prepared & (1u << (dev & 31)))) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        prepared |= 1u << (dev & 31);
+    }
+    const unsigned grid = (unsigned)((a.st.n + TICK_BLOCK - 1) / TICK_BLOCK);
+    kern<<<grid, TICK_BLOCK, smem, stream>>>(a, pose8, tag_mode, out, n_out);
+    return cudaGetLastError();
+}
+template cudaError_t launch_tick<Q_T, (Q_BIAS != 0), (Q_DIRECT != 0), (Q_MR != 0)>(const RunArgs<Q_T> &, const double *, int,
+                                                                                   double *, int, cudaStream_t);
+
 #define INST(S, PF_)                                                                                                  \
     template cudaError_t launch_run<Q_T, (Q_BIAS != 0), (Q_DIRECT != 0), S, (Q_MR != 0), PF_>(const RunArgs<Q_T> &,    \
                                                                                                unsigned, size_t, cudaStream_t);

@@ -19,7 +19,11 @@ cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStre
 
 template <typename T, bool BIAS, bool PF>
 cudaError_t launch_deliver(const DeviceState<T> &st, const Consts<T> &c, const double *pose8, int force_init,
-                           int reinit_bias, unsigned grid, size_t smem, cudaStream_t stream);
+                           int reinit_bias, int raise_ready, unsigned grid, size_t smem, cudaStream_t stream);
+
+// the fused per-tick path of the N = 1 drop-in (tick_kernel); handles without per-filter overrides
+template <typename T, bool BIAS, bool DIRECT, bool MR>
+cudaError_t launch_tick(const RunArgs<T> &a, const double *pose8, int tag_mode, double *out, int n_out, cudaStream_t stream);
 
 template <typename T, bool BIAS, bool PF>
 cudaError_t launch_predict(const DeviceState<T> &st, const Consts<T> &c, const double *u, unsigned grid, size_t smem,

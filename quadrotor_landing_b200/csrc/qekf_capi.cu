@@ -69,6 +69,10 @@ struct qekf_handle {
     // per-tick interface staging
     double *d_tick = nullptr;        // [6 imu][8 tag]
     double *h_tick = nullptr;        // pinned mirror
+    // fused per-tick path (qekf_tick): inputs [6 imu][8 tag] and the output records in MAPPED pinned memory
+    double *tick_in = nullptr, *tick_in_dev = nullptr;
+    double *tick_out = nullptr, *tick_out_dev = nullptr;
+    int tick_out_cap = 0;
     int32_t *d_no_steps = nullptr;
     double imu_latched[6] = { 0, 0, 0, 0, 0, 0 };
     // cached device copies of host streams (qekf_run with on_device = 0)
@@ -155,6 +159,9 @@ int free_state(qekf_handle *h)
     h->counts = nullptr;
     h->stats_acc = h->stats_red = nullptr; h->stats_bins = 0; h->d_shared = nullptr; h->d_shared_bytes = 0;
     if (h->h_tick) cudaFreeHost(h->h_tick);
+    if (h->tick_in) cudaFreeHost(h->tick_in);
+    if (h->tick_out) cudaFreeHost(h->tick_out);
+    h->tick_in = h->tick_in_dev = h->tick_out = h->tick_out_dev = nullptr; h->tick_out_cap = 0;
     h->x = h->P = h->aux = nullptr; h->pend = nullptr; h->flags = h->upds = nullptr;
     h->d_tick = nullptr; h->h_tick = nullptr; h->d_in = nullptr; h->d_in_bytes = 0;
     return QEKF_OK;
@@ -450,6 +457,50 @@ int rebuild_pf(qekf_handle *h)
     return h->precision == QEKF_FP64 ? rebuild_pf_t<double>(h) : rebuild_pf_t<float>(h);
 }
 
+// (re)seed the host copy of per-filter field `f` from the handle-wide parameters
+void seed_pf_field(qekf_handle *h, int f)
+{
+    static const int dims[5] = { 12, 6, 3, 4, 2 };
+    const size_t N = (size_t)h->n;
+    const qekf_params &p = h->p;
+    std::vector<double> &v = h->pf_host[f];
+    v.assign((size_t)dims[f] * N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+        if (f == QEKF_PF_Q) {
+            for (int k = 0; k < 3; ++k) {
+                v[(0 + k) * N + i] = p.Q_a[k]; v[(3 + k) * N + i] = p.Q_w[k];
+                v[(6 + k) * N + i] = p.Q_ab[k]; v[(9 + k) * N + i] = p.Q_wb[k];
+            }
+        } else if (f == QEKF_PF_R) {
+            for (int k = 0; k < 3; ++k) { v[(0 + k) * N + i] = p.R_r[k]; v[(3 + k) * N + i] = p.R_ang[k]; }
+        } else if (f == QEKF_PF_R_V_CV) {
+            for (int k = 0; k < 3; ++k) v[k * N + i] = p.r_v_cv[k];
+        } else if (f == QEKF_PF_Q_VC) {
+            for (int k = 0; k < 4; ++k) v[k * N + i] = p.q_vc[k];
+        } else {
+            v[0 * N + i] = p.measurement_delay;
+            v[1 * N + i] = p.dyn_measurement_delay_offset;
+        }
+    }
+}
+
+template <typename T, bool BIAS, bool DIRECT>
+int tick_typed(qekf_handle *h, int tag_mode, double t_curr, int n_out)
+{
+    RunArgs<T> a;
+    std::memset(&a, 0, sizeof a);
+    a.st = dstate<T>(h);
+    a.in.imu = h->tick_in_dev; a.in.cs = 1; a.in.is = 0; a.in.M = 0;
+    a.in.tag_pose = h->tick_in_dev + 6;
+    a.in.t_start = t_curr; a.in.update_freq = h->p.update_freq;
+    a.c = make_consts<T>(h->p);
+    a.k0 = 0; a.n_steps = 1; a.m0 = 0;
+    if (h->p.multirate_ekf) CUDA_TRY((launch_tick<T, BIAS, DIRECT, true>(a, h->tick_in_dev + 6, tag_mode, h->tick_out_dev, n_out, h->stream)));
+    else CUDA_TRY((launch_tick<T, BIAS, DIRECT, false>(a, h->tick_in_dev + 6, tag_mode, h->tick_out_dev, n_out, h->stream)));
+    h->launches++;
+    return QEKF_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -618,33 +669,6 @@ int qekf_get_params(const qekf_handle *h, qekf_params *p)
     return QEKF_OK;
 }
 
-// (re)seed the host copy of per-filter field `f` from the handle-wide parameters
-static void seed_pf_field(qekf_handle *h, int f)
-{
-    static const int dims[5] = { 12, 6, 3, 4, 2 };
-    const size_t N = (size_t)h->n;
-    const qekf_params &p = h->p;
-    std::vector<double> &v = h->pf_host[f];
-    v.assign((size_t)dims[f] * N, 0.0);
-    for (size_t i = 0; i < N; ++i) {
-        if (f == QEKF_PF_Q) {
-            for (int k = 0; k < 3; ++k) {
-                v[(0 + k) * N + i] = p.Q_a[k]; v[(3 + k) * N + i] = p.Q_w[k];
-                v[(6 + k) * N + i] = p.Q_ab[k]; v[(9 + k) * N + i] = p.Q_wb[k];
-            }
-        } else if (f == QEKF_PF_R) {
-            for (int k = 0; k < 3; ++k) { v[(0 + k) * N + i] = p.R_r[k]; v[(3 + k) * N + i] = p.R_ang[k]; }
-        } else if (f == QEKF_PF_R_V_CV) {
-            for (int k = 0; k < 3; ++k) v[k * N + i] = p.r_v_cv[k];
-        } else if (f == QEKF_PF_Q_VC) {
-            for (int k = 0; k < 4; ++k) v[k * N + i] = p.q_vc[k];
-        } else {
-            v[0 * N + i] = p.measurement_delay;
-            v[1 * N + i] = p.dyn_measurement_delay_offset;
-        }
-    }
-}
-
 int qekf_set_filter_params(qekf_handle *h, int field, const double *values)
 {
     static const int dims[5] = { 12, 6, 3, 4, 2 };
@@ -748,16 +772,16 @@ int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3])
     return QEKF_OK;
 }
 
-static int deliver(qekf_handle *h, int force_init, int reinit_bias)
+static int deliver(qekf_handle *h, int force_init, int reinit_bias, int raise_ready = 1)
 {
 #define CALL_DELIVER(T, B, D)                                                                                          \
     do {                                                                                                               \
         if (h->pf_on)                                                                                                  \
             CUDA_TRY((launch_deliver<T, B, true>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init,        \
-                                                 reinit_bias, grid_of(h), smem_bytes(h), h->stream)));                 \
+                                                 reinit_bias, raise_ready, grid_of(h), smem_bytes(h), h->stream)));    \
         else                                                                                                           \
             CUDA_TRY((launch_deliver<T, B, false>(dstate<T>(h), make_consts<T>(h->p), h->d_tick + 8, force_init,       \
-                                                  reinit_bias, grid_of(h), smem_bytes(h), h->stream)));                \
+                                                  reinit_bias, raise_ready, grid_of(h), smem_bytes(h), h->stream)));   \
     } while (0)
     QEKF_DISPATCH(h, CALL_DELIVER);
 #undef CALL_DELIVER
@@ -765,16 +789,31 @@ static int deliver(qekf_handle *h, int force_init, int reinit_bias)
     return QEKF_OK;
 }
 
-int qekf_set_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp)
+static int stage_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp)
 {
-    if (!h || !pos || !quat_xyzw) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));   // the pinned staging buffer is reused
     for (int i = 0; i < 3; ++i) h->h_tick[8 + i] = pos[i];
     for (int i = 0; i < 4; ++i) h->h_tick[11 + i] = quat_xyzw[i];
     h->h_tick[15] = stamp;
     CUDA_TRY(cudaMemcpyAsync(h->d_tick + 8, h->h_tick + 8, 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    return deliver(h, 0, 0);
+    return QEKF_OK;
+}
+
+int qekf_set_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp)
+{
+    if (!h || !pos || !quat_xyzw) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    int rc = stage_tag(h, pos, quat_xyzw, stamp);
+    if (rc) return rc;
+    return deliver(h, 0, 0, 1);
+}
+
+int qekf_latch_tag(qekf_handle *h, const double pos[3], const double quat_xyzw[4], double stamp)
+{
+    if (!h || !pos || !quat_xyzw) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    int rc = stage_tag(h, pos, quat_xyzw, stamp);
+    if (rc) return rc;
+    return deliver(h, 0, 0, 0);
 }
 
 int qekf_initialize_state(qekf_handle *h, int reinit_bias)
@@ -782,6 +821,44 @@ int qekf_initialize_state(qekf_handle *h, int reinit_bias)
     if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
     CUDA_TRY(cudaSetDevice(h->device));
     return deliver(h, 1, reinit_bias);
+}
+
+int qekf_tick(qekf_handle *h, const double accel[3], const double gyro[3], int tag_mode, const double tag_pos[3],
+              const double tag_quat_xyzw[4], double tag_stamp, double t_curr, int n_out, double *records)
+{
+    if (!h || !accel || !gyro) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (tag_mode < 0 || tag_mode > 2 || (tag_mode != 0 && (!tag_pos || !tag_quat_xyzw)))
+        return fail(QEKF_ERR_BAD_ARG, "bad tag_mode, or a tag without a pose");
+    if (n_out < 0 || n_out > h->n || n_out > 4096 || (n_out > 0 && !records)) return fail(QEKF_ERR_BAD_ARG, "bad record count");
+    if (h->pf_on) return fail(QEKF_ERR_BAD_ARG, "qekf_tick does not serve handles with per-filter parameter overrides");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->tick_in) {
+        CUDA_TRY(cudaHostAlloc(&h->tick_in, 16 * sizeof(double), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&h->tick_in_dev, h->tick_in, 0));
+    }
+    if (n_out > h->tick_out_cap) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->tick_out) cudaFreeHost(h->tick_out);
+        h->tick_out = nullptr; h->tick_out_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&h->tick_out, (size_t)n_out * TICK_REC * sizeof(double), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&h->tick_out_dev, h->tick_out, 0));
+        h->tick_out_cap = n_out;
+    }
+    // (the previous tick ended with a stream synchronisation, so the mapped input words are free)
+    for (int i = 0; i < 3; ++i) { h->tick_in[i] = accel[i]; h->tick_in[3 + i] = gyro[i]; h->imu_latched[i] = accel[i]; h->imu_latched[3 + i] = gyro[i]; }
+    if (tag_mode != 0) {
+        for (int i = 0; i < 3; ++i) h->tick_in[6 + i] = tag_pos[i];
+        for (int i = 0; i < 4; ++i) h->tick_in[9 + i] = tag_quat_xyzw[i];
+        h->tick_in[13] = tag_stamp;
+    }
+    int rc = QEKF_OK;
+#define CALL_TICK(T, B, D) rc = tick_typed<T, B, D>(h, tag_mode, t_curr, n_out)
+    QEKF_DISPATCH(h, CALL_TICK);
+#undef CALL_TICK
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (n_out > 0) std::memcpy(records, h->tick_out, (size_t)n_out * TICK_REC * sizeof(double));
+    return QEKF_OK;
 }
 
 int qekf_filter_update(qekf_handle *h, double t_curr)

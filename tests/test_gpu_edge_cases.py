@@ -106,3 +106,58 @@ def test_statistics_count_divergence():
     s = b.stats()
     assert s[-1, 18] == N and s[-1, 16] == 0          # all diverged, none sampled
     b.close()
+
+
+def test_rejected_per_filter_override_leaves_the_handle_untouched():
+    """A first qekf_set_filter_params call that fails validation must not switch the per-filter tables on (they would be
+    uninitialised): the next replay still uses the handle-wide parameters."""
+    p = rotors_params(q.default_params())
+    p.multirate_ekf = 1
+    scn = scenario.generate(p)
+    N, T = 40, 600
+    st = noisy_streams(scn, N, seed=4, T=T)
+    ref = q.BatchEKF(p, N)
+    ref.run(0, T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    b = q.BatchEKF(p, N)
+    bad = np.zeros((2, N)); bad[0] = -1.0                      # negative measurement_delay
+    with pytest.raises(q.QekfError):
+        b.set_filter_params(q.PF_DELAY, bad)
+    b.run(0, T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    assert norm_rel(b.state(), ref.state()) == 0 and norm_rel(b.cov(), ref.cov()) == 0
+    ref.close(); b.close()
+
+
+def test_set_params_reaches_the_fields_that_were_never_overridden():
+    """Q is overridden per filter, R is not: a later qekf_set_params with a new R must be used by every filter
+    (include/qekf.h: fields never overridden keep the handle-wide value)."""
+    p = rotors_params(q.default_params())
+    scn = scenario.generate(p)
+    N, T = 33, 800
+    st = noisy_streams(scn, N, seed=6, T=T)
+    Q = np.array(list(p.Q_a) + list(p.Q_w) + list(p.Q_ab) + list(p.Q_wb))[:, None] * np.linspace(0.5, 2.0, N)[None, :]
+    p2 = rotors_params(q.default_params())
+    for i in range(3):
+        p2.R_r[i] *= 4.0
+        p2.R_ang[i] *= 0.25
+    b = q.BatchEKF(p, N)
+    b.set_filter_params(q.PF_Q, Q)
+    b.set_params(p2)
+    b.run(0, T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    ob = orc.Batch(orc.params_from(p2), N)
+    ob.set_filter_params(orc.PF_Q, Q)
+    ob.run(0, T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    assert norm_rel(b.state(), ob.state()) < 1e-9 and norm_rel(b.cov(), ob.cov()) < 1e-9
+    b.close()
+
+
+def test_forced_initialisation_before_any_tag_uses_the_identity_orientation():
+    """initialize_state with no detection latched yet: apriltag_orien is the constructor's identity (cpp:14), so the
+    nominal attitude becomes conj(q_vc) instead of a zero quaternion."""
+    p = rotors_params(q.default_params())
+    b = q.BatchEKF(p, 3)
+    b.initialize_state(False)
+    f = orc.Filter(orc.params_from(p))
+    f.initialize_state(False)
+    x = b.state()
+    assert np.all(np.isfinite(x)) and norm_rel(x[:, 0], f.state()) < 1e-12
+    b.close()

@@ -76,3 +76,61 @@ def test_replay_driver_matches_oracle(tmp_path, preset, extra, overrides):
                 assert abs(v[64] - aux["measurement_delay_curr"]) < 1e-12
     assert n_active > 0.9 * T and n_corr > 20, log
     assert worst < TOL, worst
+
+
+def test_facade_tick_latency_is_far_below_the_timer_period(tmp_path):
+    """RelativePoseEKF::filter_update through the facade = one launch + one stream synchronisation (qekf_tick).  The node's
+    timer runs at update_freq (relative_pose_EKF_node.cpp:50): at 200 Hz a tick has 5,000 us; the bar here is p99 < 1,000 us
+    (5x margin), single-rate and delayed fusion."""
+    import json
+    for extra in (["--single-rate", "--update-freq", "200", "--measurement-freq", "30", "--seconds", "10"],
+                  ["--update-freq", "200", "--measurement-freq", "30", "--seconds", "10", "--latency", "0.03"]):
+        _, _, _, log = run_driver(tmp_path, "rotors_sim.yaml", extra)
+        line = [ln for ln in log.splitlines() if "tick_latency_us" in ln][-1]
+        lat = json.loads(line.split("qekf_replay: ", 1)[1])["tick_latency_us"]
+        print("tick latency", extra[0], lat)
+        assert lat["ticks"] >= 1500 and lat["p99"] < 1000.0 and lat["median"] < 500.0
+
+
+def test_fused_tick_equals_the_separate_calls():
+    """qekf_tick == qekf_set_tag + qekf_set_imu + qekf_filter_update + the four getters, bit for bit, for a small batch
+    (all filters get the same inputs), single-rate and delayed fusion with dynamic delay."""
+    import ctypes as C
+    from quadrotor_landing_b200 import _native as nat
+    from quadrotor_landing_b200 import scenario
+    from streams_np import noisy_streams, rotors_params
+    L = nat.lib()
+    dp = C.POINTER(C.c_double)
+    for mr in (0, 1):
+        p = rotors_params(q.default_params())
+        p.multirate_ekf, p.dynamic_meas_delay = mr, mr
+        scn = scenario.generate(p)
+        st = noisy_streams(scn, 1, seed=3, T=900)
+        a, b = q.BatchEKF(p, 5), q.BatchEKF(p, 5)
+        arrivals = {int(k): m for m, k in enumerate(st["tag_step"])}
+        rec = np.zeros((3, 258))
+        for k in range(900):
+            t = k / p.update_freq
+            u = np.ascontiguousarray(st["imu"][k, :, 0])
+            mode = 0
+            pose = np.zeros(7); stamp = 0.0
+            if k in arrivals and st["tag_valid"][arrivals[k], 0]:
+                m = arrivals[k]
+                pose = np.ascontiguousarray(st["tag_pose"][m, :, 0]); stamp = float(st["tag_stamp"][m]) - 0.02 * mr
+                a.set_tag(pose[0:3], pose[3:7], stamp)
+                mode = 1
+            a.set_imu(u[0:3], u[3:6])
+            a.filter_update(t)
+            acc, gyr, pos, quat = (np.ascontiguousarray(v) for v in (u[0:3], u[3:6], pose[0:3], pose[3:7]))
+            nat.check(L.qekf_tick(b._h, acc.ctypes.data_as(dp), gyr.ctypes.data_as(dp), mode, pos.ctypes.data_as(dp),
+                                  quat.ctypes.data_as(dp), stamp, t, 3, rec.ctypes.data_as(dp)))
+            if k % 37 == 0 or k == 899:
+                x, P, aux, fl = a.state(0, 3), a.cov(0, 3), a.aux(0, 3), a.flags(0, 3)
+                n = a.n
+                for j in range(3):
+                    assert np.array_equal(rec[j, 0:16], x[:, j])
+                    assert np.array_equal(rec[j, 16:16 + n * n].reshape(n, n), P[:, :, j])
+                    assert np.array_equal(rec[j, 241:252], aux[:, j])
+                    assert np.array_equal(rec[j, 252:258].astype(np.int32), fl[:, j])
+        assert np.array_equal(a.state(), b.state()) and np.array_equal(a.cov(), b.cov())
+        a.close(); b.close()

@@ -12,6 +12,7 @@
 //
 //   qekf_replay --preset FILE.yaml [--update-freq HZ] [--measurement-freq HZ] [--tag-rate HZ] [--seconds S]
 //               [--latency S] [--seed N] [--single-rate] [--fixed-delay] [--out trace.csv] [--dump-streams PREFIX]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -132,6 +133,8 @@ int main(int argc, char **argv)
 
         int64_t m = 0;
         long corrections = 0;
+        std::vector<double> tick_us;
+        tick_us.reserve((size_t)T);
         for (int64_t k = 0; k < T; ++k) {
             const double t_now = sc.t_start + (double)k / rel_pose_ekf.update_freq;
             // ---- AprilTagSubCallback (node.cpp:153-176) ----
@@ -159,6 +162,7 @@ int main(int argc, char **argv)
             }
             // ---- FilterUpdateCallback (node.cpp:178-283) ----
             rel_pose_ekf.filter_update(t_now);
+            tick_us.push_back(rel_pose_ekf.last_tick_seconds * 1e6);
             std::fprintf(out, "%lld,%.17g,%d", (long long)k, t_now, (int)rel_pose_ekf.filter_active);
             if (!rel_pose_ekf.filter_active) { std::fprintf(out, "\n"); continue; }
             std::fprintf(out, ",%.17g,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g", rel_pose_ekf.r_nom(0), rel_pose_ekf.r_nom(1),
@@ -188,6 +192,14 @@ int main(int argc, char **argv)
         std::printf("qekf_replay: %lld ticks, %ld corrections; final position error %.4f %.4f %.4f m; trace -> %s\n",
                     (long long)T, corrections, rel_pose_ekf.r_nom(0) - tr[0], rel_pose_ekf.r_nom(1) - tr[1],
                     rel_pose_ekf.r_nom(2) - tr[2], opt.out.c_str());
+        // host latency of RelativePoseEKF::filter_update (one launch + one synchronisation), first 200 ticks left out
+        if (tick_us.size() > 400) {
+            std::vector<double> v(tick_us.begin() + 200, tick_us.end());
+            std::sort(v.begin(), v.end());
+            std::printf("qekf_replay: {\"tick_latency_us\": {\"median\": %.2f, \"p99\": %.2f, \"max\": %.2f, \"ticks\": %zu, "
+                        "\"tick_period_us\": %.1f}}\n", v[v.size() / 2], v[(size_t)((double)v.size() * 0.99)], v.back(), v.size(),
+                        1e6 / rel_pose_ekf.update_freq);
+        }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qekf_replay: %s\n", e.what());
         return 2;
