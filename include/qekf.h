@@ -196,6 +196,21 @@ int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6
  * x16 [16][count], P [n*n][count] (upper triangle is used).  Checkpoint/resume and step tests. */
 int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x16, const double *P);
 
+/* ---- exact checkpoint / resume (no reference equivalent: the reference restarts from its constructor) ----
+ * qekf_export_state writes everything a later tick depends on into one HOST blob of qekf_export_size(h) bytes:
+ * nominal state, covariance, aux, the latched tag pose + stamp, flags, upds_since_correction, the latched IMU sample,
+ * step counters, and -- with multirate_ekf -- the delayed-fusion history in the form the handle keeps it (lagged
+ * checkpoint, ring of IMU inputs, ring head, entries after the checkpoint, x_hist.size(); together they determine
+ * every entry of the reference's x_hist / u_hist / P_hist vectors, relative_pose_EKF.cpp:196-264), plus the
+ * Monte-Carlo statistics accumulators when configured.  Arrays travel verbatim in the handle's precision, so
+ * export -> destroy -> create (same params, N, precision, per-filter overrides) -> import -> run continues
+ * bit-identically to the uninterrupted run, single-rate and delayed fusion alike (unlike qekf_set_state, which
+ * restarts the history from the given entry).  qekf_import_state rejects a blob whose size, precision, parameters or
+ * history geometry differ from the receiving handle's. */
+int64_t qekf_export_size(const qekf_handle *h);
+int qekf_export_state(qekf_handle *h, void *buf, int64_t bytes);
+int qekf_import_state(qekf_handle *h, const void *buf, int64_t bytes);
+
 /* ---- stateless step functions over a batch (private methods of the reference class) ----------- */
 /* prediction_step (src/relative_pose_EKF.cpp:346-415) applied to the handle's current state with
  * per-filter inputs u [6][N] (host).  Writes accel_rel. */
@@ -258,6 +273,8 @@ int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const 
  *   [18] diverged samples (non-finite state or covariance not SPD)  [19] sum |dr|^2 */
 #define QEKF_STAT_DIM 20
 int qekf_stats_configure(qekf_handle *h, int32_t n_bins, int32_t stride);
+/* The current configuration (0, 0 when statistics are not configured; qekf_import_state may have configured them). */
+int qekf_stats_config(const qekf_handle *h, int32_t *n_bins, int32_t *stride);
 int qekf_stats_reset(qekf_handle *h);
 int qekf_get_stats(qekf_handle *h, double *out /* host [n_bins][QEKF_STAT_DIM] */);
 /* Reduced statistics copied into a caller-owned DEVICE buffer [n_bins][QEKF_STAT_DIM] on the handle's

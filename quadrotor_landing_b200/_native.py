@@ -133,6 +133,7 @@ EXPORTS = [
     "qekf_stats_reset", "qekf_get_stats", "qekf_copy_stats_device",
     "qekf_reset_filters", "qekf_launch_count", "qekf_measure_fma_peak", "qekf_step_counts",
     "qekf_params_from_yaml", "qekf_params_from_yaml_text",
+    "qekf_export_size", "qekf_export_state", "qekf_import_state", "qekf_stats_config",
 ]
 
 _lib = None
@@ -185,6 +186,7 @@ def lib() -> C.CDLL:
                                           C.c_int64, dp, dp, C.POINTER(C.c_uint8), dp]
     L.qekf_stats_configure.argtypes = [vp, C.c_int32, C.c_int32]
     L.qekf_stats_reset.argtypes = [vp]
+    L.qekf_stats_config.argtypes = [vp, ip, ip]
     L.qekf_get_stats.argtypes = [vp, dp]
     L.qekf_copy_stats_device.argtypes = [vp, vp]
     L.qekf_reset_filters.argtypes = [vp]
@@ -192,6 +194,10 @@ def lib() -> C.CDLL:
     L.qekf_launch_count.restype = C.c_int64
     L.qekf_measure_fma_peak.argtypes = [C.c_int, C.c_int, dp]
     L.qekf_step_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+    L.qekf_export_size.argtypes = [vp]
+    L.qekf_export_size.restype = C.c_int64
+    L.qekf_export_state.argtypes = [vp, vp, C.c_int64]
+    L.qekf_import_state.argtypes = [vp, vp, C.c_int64]
     L.qekf_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(QekfParams)]
     L.qekf_params_from_yaml_text.argtypes = [C.c_char_p, C.POINTER(QekfParams)]
     _lib = L

@@ -416,6 +416,30 @@ QEKF_FN bool cta_any(bool x)
 #endif
 }
 
+// An int32 that lives in the lane's slot of a shared-memory scratch array.  Whatever the replay loops carry from
+// one iteration to the next competes with the ~200 registers of the unrolled tick; what loses ends up in local
+// memory, and with 7 warps per SM and an L1 that shared memory has squeezed to a few KB the reloads are L2 round
+// trips on the critical path of every tick (profiles/r1_05_sr_vs_multirate.md: 73 local loads per warp-tick in the
+// delayed-fusion loop; profiles/r2_06_sr_stalls.md: the tick index, the prediction counter, the prefetched IMU sample and
+// the true bias in the single-rate loop).  The sequencer's integer state and the true bias' six normals are therefore
+// kept here explicitly: a shared-memory access costs a tenth of that.
+struct SmemInt {
+    int32_t *p;
+    QEKF_FN operator int32_t() const { return *p; }
+    QEKF_FN SmemInt &operator=(int32_t v) { *p = v; return *this; }
+    QEKF_FN SmemInt &operator=(const SmemInt &o) { *p = *o.p; return *this; }   // assigns the value, not the slot
+    QEKF_FN SmemInt &operator+=(int32_t v) { *p += v; return *this; }
+    QEKF_FN SmemInt &operator-=(int32_t v) { *p -= v; return *this; }
+    QEKF_FN SmemInt &operator|=(int32_t v) { *p |= v; return *this; }
+    QEKF_FN SmemInt &operator&=(int32_t v) { *p &= v; return *this; }
+    QEKF_FN SmemInt &operator++() { *p += 1; return *this; }
+};
+// per-lane scratch words of the replay loops:
+//   delayed fusion: flags upds nh hpos hlen m next_tag_step pend_m held k | 6 floats: the true bias' normals
+//   single rate   : flags upds n_pred n_corr n_iter m next_tag_step pend_m held k | 6 floats: the true bias' normals
+constexpr int MR_SCRATCH_INTS = 16;
+constexpr int SR_SCRATCH_INTS = 16;
+
 // The per-filter replay loop, one lane per filter.  Host-callable so that the CPU-side unit tests
 // (tests/host_core) can run the very same code against the oracle without a GPU; the product only ever
 // calls it from run_kernel.
@@ -432,18 +456,23 @@ QEKF_FN bool cta_any(bool x)
 // sample together (one execution of the sampling code per stride; the time skew is back to zero).
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
-QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bool live = true, int *vbuf = nullptr)
+QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
+                        const bool live = true, int *vbuf = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
     const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
-    const int64_t k_end = a.k0 + a.n_steps;
+    const int32_t k_end = (int32_t)(a.k0 + a.n_steps);       // (qekf_run bounds tick indices to 31 bits)
     Nominal<T> s;
-    int32_t flags = 0, upds = 0;
+    SmemInt flags{ scr + 0 * scr_stride }, upds{ scr + 1 * scr_stride }, n_pred{ scr + 2 * scr_stride };
+    SmemInt n_corr{ scr + 3 * scr_stride }, n_iter{ scr + 4 * scr_stride }, m{ scr + 5 * scr_stride };
+    SmemInt next_tag_step{ scr + 6 * scr_stride }, pend_m{ scr + 7 * scr_stride }, held{ scr + 8 * scr_stride };
+    SmemInt k{ scr + 9 * scr_stride };
+    flags = 0; upds = 0; n_pred = 0; n_corr = 0; n_iter = 0;
     T accel[3] = { T(0), T(0), T(0) };
     Inputs<T, SYNTH> in;
     double un[6] = { 0, 0, 0, 0, 0, 0 };
-    int64_t k = k_end;                 // padding lanes are born finished
+    k = k_end;                         // padding lanes are born finished
     if (live) {
         load_filter<T>(a.st, i, s, P);
         flags = a.st.flags[i];
@@ -451,15 +480,27 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
         in.init(a, i);
-        k = a.k0;
-        in.raw_imu(k, un);             // software prefetch: un always holds the raw sample of tick k
+        k = (int32_t)a.k0;
+        if (SYNTH) {                   // the true bias as its six normals, in the scratch
+            float z[6];
+            normals6(a.ns, in.gid, STREAM_BIAS, 0u, z);
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) reinterpret_cast<float *>(scr)[(10 + cc) * scr_stride] = z[cc];
+        } else {
+            in.raw_imu(k, un);         // software prefetch (explicit streams live in HBM): un holds the raw sample of tick k
+        }
     }
+    auto true_bias_now = [&](double b[6]) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc)
+            b[cc] = (double)(cc < 3 ? a.ns.sig_ba : a.ns.sig_bw) * (double)reinterpret_cast<const float *>(scr)[(10 + cc) * scr_stride];
+    };
 
-    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0, n_cev = 0;
-    int32_t m = a.m0;
-    int32_t next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
-    int32_t pend_m = -1;               // index of the latched arrival; -1 = latched pose lives in st.pend
-    int32_t held = 0;                  // iterations this lane has held its correction tick back
+    uint32_t n_sexec = 0, n_cev = 0;
+    m = a.m0;
+    next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+    pend_m = -1;                       // index of the latched arrival; -1 = latched pose lives in st.pend
+    held = 0;                          // iterations this lane has held its correction tick back
     bool at_fence = false;             // finished a sampling tick; waiting for the warp to catch up
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
@@ -485,22 +526,25 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         }
 
         // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
-        const bool want = active && (flags & FLAG_INIT) && (flags & FLAG_READY) &&
+        const int32_t fl0 = flags;
+        const bool want = active && (fl0 & FLAG_INIT) && (fl0 & FLAG_READY) &&
                           (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
         const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
         if (v.active == 0 && v.at_fence == 0) break;     // every lane of the CTA has finished
         ++n_iter;
         if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
             // every lane is at the fence (or finished): sample together, then resume on the next iteration
-            const bool mine = live && at_fence && (flags & FLAG_INIT);
-            stats_sample<T, BIAS>(a, i, k - 1, s, P, in.bias, mine);
+            const bool mine = live && at_fence && (fl0 & FLAG_INIT);
+            double tb[6] = { 0, 0, 0, 0, 0, 0 };
+            if (SYNTH) true_bias_now(tb);
+            stats_sample<T, BIAS>(a, i, (int64_t)k - 1, s, P, tb, mine);
             if (mine) ++n_sexec;
             at_fence = false;
         }
         bool serve = true;
         if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
         if (want && !serve) ++held;                      // hold tick k back; nothing has been consumed
-        const bool exec = active && !(want && !serve) && (flags & FLAG_INIT);
+        const bool exec = active && !(want && !serve) && (fl0 & FLAG_INIT);
 
         // ---- consume the measurement, corner-margin gate (cpp:150-186) ----
         bool perform = false;
@@ -523,7 +567,18 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
             // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
             T u[6];
-            in.imu(k, un, u);
+            if (SYNTH) {
+                // the clean sample is shared by all filters (L1 / L2 resident) and is fetched here, at its use: the Philox
+                // rounds of the noise cover the load, and nothing has to be carried across the iteration
+                double raw[6], tb[6], ud[6];
+                in.raw_imu(a.in, k, raw);
+                true_bias_now(tb);
+                synth_imu(a.ns, in.gid, k, raw, tb, ud);
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
+            } else {
+                in.imu(k, un, u);
+            }
             prediction_step<T, BIAS>(s, P, u, par, accel);
             ++n_pred;
             if (perform) {
@@ -548,7 +603,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
         }
         if (active && !(want && !serve)) {
             ++k;
-            if (k < k_end) in.raw_imu(k, un);
+            if (!SYNTH && k < k_end) in.raw_imu(k, un);
             if (do_stats && (k % a.stats.stride) == 0) at_fence = true;   // tick k-1 was a sampling tick
         }
     }
@@ -567,16 +622,16 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
     a.st.upds[i] = upds;
     if (a.st.counts) {
 #ifdef __CUDA_ARCH__
-        atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
-        atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
+        atomicAdd(a.st.counts + 0, (unsigned long long)(uint32_t)(int32_t)n_pred);
+        atomicAdd(a.st.counts + 1, (unsigned long long)(uint32_t)(int32_t)n_corr);
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);   // loop iterations per warp
+            atomicAdd(a.st.counts + 2, (unsigned long long)(uint32_t)(int32_t)n_iter);   // loop iterations per warp
             atomicAdd(a.st.counts + 3, (unsigned long long)n_cev);    // ... of which the warp ran the correction
         }
         atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
 #else
-        a.st.counts[0] += n_pred;
-        a.st.counts[1] += n_corr;
+        a.st.counts[0] += (uint32_t)(int32_t)n_pred;
+        a.st.counts[1] += (uint32_t)(int32_t)n_corr;
 #endif
     }
 #pragma unroll
@@ -586,23 +641,6 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, const bo
 // ------------------------------------------------------------------------------------------------
 // delayed-measurement fusion (multirate_ekf = true), evaluated lazily
 // ------------------------------------------------------------------------------------------------
-// An int32 that lives in the lane's slot of a shared-memory scratch array.  The multirate loop calls three
-// out-of-line functions per iteration; everything that is live across a call ends up in local memory (the ABI
-// keeps few registers across calls), and with 7 warps per SM the L2 round trips of those reloads sat on the
-// critical path of every light tick (73 local loads per warp-tick, long-scoreboard 2.9 per issue).  The
-// sequencer's integer state is therefore kept here explicitly: a shared-memory access costs a tenth of that.
-struct SmemInt {
-    int32_t *p;
-    QEKF_FN operator int32_t() const { return *p; }
-    QEKF_FN SmemInt &operator=(int32_t v) { *p = v; return *this; }
-    QEKF_FN SmemInt &operator=(const SmemInt &o) { *p = *o.p; return *this; }   // assigns the value, not the slot
-    QEKF_FN SmemInt &operator+=(int32_t v) { *p += v; return *this; }
-    QEKF_FN SmemInt &operator-=(int32_t v) { *p -= v; return *this; }
-    QEKF_FN SmemInt &operator|=(int32_t v) { *p |= v; return *this; }
-    QEKF_FN SmemInt &operator&=(int32_t v) { *p &= v; return *this; }
-    QEKF_FN SmemInt &operator++() { *p += 1; return *this; }
-};
-constexpr int MR_SCRATCH_INTS = 16;   // flags upds nh hpos hlen m next_tag_step pend_m held k | 6 floats: the true bias' normals
 template <typename T, class PS>
 QEKF_FN void load_checkpoint(const DeviceState<T> &st, int64_t i, Nominal<T> &s, PS &P)
 {
@@ -900,7 +938,7 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
         // the sequencer's integers live in the shared memory behind the vote words
         run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, live, vbuf);
     } else {
-        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, live, vbuf);
+        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, live, vbuf);
     }
 }
 
@@ -981,7 +1019,7 @@ __global__ void __launch_bounds__(TICK_BLOCK) tick_kernel(const __grid_constant_
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)TICK_BLOCK * (N * (N + 1) / 2));
     if (live && tag_mode != 0) deliver_one<T, BIAS, false>(a.st, a.c, pose8, 0, 0, tag_mode == 1, P, i);
     if (MR) run_filter_mr<T, BIAS, DIRECT, false, false>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, TICK_BLOCK, live, vbuf);
-    else run_filter<T, BIAS, DIRECT, false, false>(a, i, P, live, vbuf);
+    else run_filter<T, BIAS, DIRECT, false, false>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, TICK_BLOCK, live, vbuf);
     if (live && i < n_out) {
         const DeviceState<T> &st = a.st;
         double *r = out + i * TICK_REC;

@@ -21,7 +21,7 @@ cudaError_t launch_tick(const RunArgs<T> &a, const double *pose8, int tag_mode, 
     constexpr int N = BIAS ? 15 : 9;
     auto kern = tick_kernel<T, BIAS, DIRECT, MR>;
     const size_t smem = (size_t)TICK_BLOCK * (N * (N + 1) / 2) * sizeof(T) + VOTE_WORDS * sizeof(int) +
-                        (MR ? (size_t)TICK_BLOCK * MR_SCRATCH_INTS * sizeof(int32_t) : 0);
+                        (size_t)TICK_BLOCK * (MR ? MR_SCRATCH_INTS : SR_SCRATCH_INTS) * sizeof(int32_t);
     static unsigned prepared = 0;          // per instantiation and device: the attribute call is not free on a 200 Hz path
     int dev = 0;
     cudaGetDevice(&dev);

@@ -122,7 +122,7 @@ int block_of(const qekf_handle *h) { return h->precision == QEKF_FP64 ? BlockOf<
 size_t smem_bytes(const qekf_handle *h)
 {
     size_t b = (size_t)block_of(h) * h->np * h->tsize + VOTE_WORDS * sizeof(int);
-    if (h->p.multirate_ekf) b += (size_t)block_of(h) * MR_SCRATCH_INTS * sizeof(int32_t);
+    b += (size_t)block_of(h) * (h->p.multirate_ekf ? MR_SCRATCH_INTS : SR_SCRATCH_INTS) * sizeof(int32_t);
     return b;
 }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + block_of(h) - 1) / block_of(h)); }
@@ -1029,6 +1029,114 @@ int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x
     return QEKF_OK;
 }
 
+// ---- exact checkpoint / resume ---------------------------------------------------------------------------
+// Everything a later run depends on, as one flat host blob: the device arrays of the handle verbatim (in the
+// handle's own precision and padded layout, so nothing is rounded or reordered) behind a header that pins what the
+// receiving handle must look like.
+
+namespace {
+
+struct ExportHeader {
+    char magic[8];                 // "QEKFCKP1"
+    int32_t precision, nstates, multirate, ring_len, dmax, stats_bins, stats_stride, reserved;
+    int64_t n, ld, total_bytes;
+    double imu_latched[6];
+    qekf_params p;
+};
+
+struct Segment { void *dev; size_t bytes; };
+
+std::vector<Segment> export_segments(const qekf_handle *h)
+{
+    const size_t ld = (size_t)h->ld, ts = h->tsize;
+    std::vector<Segment> v = {
+        { h->x, 16 * ld * ts }, { h->P, (size_t)h->np * ld * ts }, { h->aux, AUX_DIM * ld * ts },
+        { h->pend, PEND_DIM * ld * sizeof(double) }, { h->flags, ld * sizeof(int32_t) }, { h->upds, ld * sizeof(int32_t) },
+        { h->counts, 8 * sizeof(unsigned long long) } };
+    if (h->xc) {
+        v.push_back({ h->xc, 16 * ld * ts });
+        v.push_back({ h->Pc, (size_t)h->np * ld * ts });
+        v.push_back({ h->ring, (size_t)h->ring_len * 6 * ld * ts });
+        v.push_back({ h->nh, ld * sizeof(int32_t) });
+        v.push_back({ h->hpos, ld * sizeof(int32_t) });
+        v.push_back({ h->hlen, ld * sizeof(int32_t) });
+    }
+    if (h->stats_acc) v.push_back({ h->stats_acc, (size_t)STAT_REPL * h->stats_bins * STAT_DIM * 8 });
+    return v;
+}
+
+}  // namespace
+
+int64_t qekf_export_size(const qekf_handle *h)
+{
+    if (!h) return 0;
+    size_t b = sizeof(ExportHeader);
+    for (const Segment &s : export_segments(h)) b += s.bytes;
+    return (int64_t)b;
+}
+
+int qekf_export_state(qekf_handle *h, void *buf, int64_t bytes)
+{
+    if (!h || !buf) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    const int64_t need = qekf_export_size(h);
+    if (bytes < need) return fail(QEKF_ERR_BAD_ARG, "export buffer is smaller than qekf_export_size()");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    ExportHeader hd;
+    std::memset(&hd, 0, sizeof hd);
+    std::memcpy(hd.magic, "QEKFCKP1", 8);
+    hd.precision = h->precision; hd.nstates = h->nstates; hd.multirate = h->xc ? 1 : 0;
+    hd.ring_len = h->ring_len; hd.dmax = h->dmax;
+    hd.stats_bins = h->stats_acc ? h->stats_bins : 0; hd.stats_stride = h->stats_acc ? h->stats_stride : 0;
+    hd.n = h->n; hd.ld = h->ld; hd.total_bytes = need;
+    std::memcpy(hd.imu_latched, h->imu_latched, sizeof hd.imu_latched);
+    hd.p = h->p;
+    unsigned char *out = static_cast<unsigned char *>(buf);
+    std::memcpy(out, &hd, sizeof hd);
+    size_t off = sizeof hd;
+    for (const Segment &s : export_segments(h)) {
+        CUDA_TRY(cudaMemcpy(out + off, s.dev, s.bytes, cudaMemcpyDeviceToHost));
+        off += s.bytes;
+    }
+    return QEKF_OK;
+}
+
+int qekf_import_state(qekf_handle *h, const void *buf, int64_t bytes)
+{
+    if (!h || !buf) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    if (bytes < (int64_t)sizeof(ExportHeader)) return fail(QEKF_ERR_BAD_ARG, "blob is shorter than its header");
+    ExportHeader hd;
+    std::memcpy(&hd, buf, sizeof hd);
+    if (std::memcmp(hd.magic, "QEKFCKP1", 8) != 0) return fail(QEKF_ERR_BAD_ARG, "not a qekf_export_state blob");
+    if (hd.total_bytes > bytes) return fail(QEKF_ERR_BAD_ARG, "blob is truncated");
+    if (hd.n != h->n || hd.ld != h->ld || hd.precision != h->precision || hd.nstates != h->nstates)
+        return fail(QEKF_ERR_BAD_ARG, "blob was exported from a handle of another size, precision or est_bias");
+    if (std::memcmp(&hd.p, &h->p, sizeof(qekf_params)) != 0)
+        return fail(QEKF_ERR_BAD_ARG, "blob was exported under other parameters (create the handle with the same qekf_params)");
+    if (hd.multirate != (h->xc ? 1 : 0) || hd.ring_len != h->ring_len || hd.dmax != h->dmax)
+        return fail(QEKF_ERR_BAD_ARG, "delayed-fusion history of the blob does not fit this handle (apply the same per-filter "
+                                      "delay overrides before importing)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (hd.stats_bins > 0 && (!h->stats_acc || h->stats_bins != hd.stats_bins || h->stats_stride != hd.stats_stride)) {
+        int rc = qekf_stats_configure(h, hd.stats_bins, hd.stats_stride);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<Segment> segs = export_segments(h);
+    if (hd.stats_bins == 0 && h->stats_acc) segs.pop_back();      // the blob carries no accumulators: keep ours
+    size_t need = sizeof hd;
+    for (const Segment &s : segs) need += s.bytes;
+    if ((int64_t)need != hd.total_bytes) return fail(QEKF_ERR_BAD_ARG, "blob size does not match this handle's layout");
+    const unsigned char *in = static_cast<const unsigned char *>(buf);
+    size_t off = sizeof hd;
+    for (const Segment &s : segs) {
+        CUDA_TRY(cudaMemcpy(s.dev, in + off, s.bytes, cudaMemcpyHostToDevice));
+        off += s.bytes;
+    }
+    std::memcpy(h->imu_latched, hd.imu_latched, sizeof hd.imu_latched);
+    return QEKF_OK;
+}
+
 // ---- stateless step functions ------------------------------------------------------------------------
 
 static int stage_rows(qekf_handle *h, const double *host, int rows)
@@ -1261,6 +1369,14 @@ int qekf_stats_configure(qekf_handle *h, int32_t n_bins, int32_t stride)
     CUDA_TRY(cudaMalloc(&h->stats_red, (size_t)n_bins * STAT_DIM * 8));
     h->stats_bins = n_bins; h->stats_stride = stride;
     return qekf_stats_reset(h);
+}
+
+int qekf_stats_config(const qekf_handle *h, int32_t *n_bins, int32_t *stride)
+{
+    if (!h || !n_bins || !stride) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
+    *n_bins = h->stats_acc ? h->stats_bins : 0;
+    *stride = h->stats_acc ? h->stats_stride : 0;
+    return QEKF_OK;
 }
 
 int qekf_stats_reset(qekf_handle *h)

@@ -255,6 +255,23 @@ class BatchEKF:
         Pm = _f64(P).reshape(n * n, count)
         check(self._L.qekf_set_state(self._h, first, count, _dp(x), _dp(Pm)))
 
+    def export_state(self) -> np.ndarray:
+        """Exact checkpoint (qekf_export_state): state, covariance, latched inputs, flags, counters, the delayed-fusion
+        history and the statistics accumulators as one host blob."""
+        n = int(self._L.qekf_export_size(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        check(self._L.qekf_export_state(self._h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf
+
+    def import_state(self, blob):
+        """Resume from an export_state() blob of a handle with the same parameters, size and precision."""
+        buf = np.ascontiguousarray(blob, dtype=np.uint8)
+        check(self._L.qekf_import_state(self._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+        nb, stride = C.c_int32(), C.c_int32()
+        check(self._L.qekf_stats_config(self._h, C.byref(nb), C.byref(stride)))
+        if nb.value:
+            self._stats_bins = nb.value
+
 
 class RelativePoseEKF:
     """The reference's single estimator, same member names, backed by a batch of one on the GPU.

@@ -194,11 +194,11 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
     const bool synth = mc && mc->ns;
     for (int64_t i = 0; i < N; ++i) {
         PLocal<T, NS> P;
-        int32_t mr_ints[MR_SCRATCH_INTS];
+        int32_t mr_ints[MR_SCRATCH_INTS > SR_SCRATCH_INTS ? MR_SCRATCH_INTS : SR_SCRATCH_INTS];
 #define RUN_(S, F)                                                         \
         do {                                                               \
             if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P, mr_ints, 1); \
-            else run_filter<T, BIAS, DIRECT, S, F>(a, i, P);               \
+            else run_filter<T, BIAS, DIRECT, S, F>(a, i, P, mr_ints, 1);   \
         } while (0)
         if (synth && pf) RUN_(true, true);
         else if (synth) RUN_(true, false);
