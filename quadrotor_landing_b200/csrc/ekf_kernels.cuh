@@ -54,7 +54,13 @@ template <typename T> struct DeviceState {
     // host orders filters by the start of their private tag dropout, so that the filters sharing a CTA lose and
     // regain their measurements together and their correction cadence stays aligned; filters are independent and
     // the noise is keyed by the filter id, so the order changes no result.
+    //   perm     : index indirection -- slot j works on row perm[j] of every array (the cooperative mappings, ekf_coop.cuh /
+    //              ekf_duo.cuh; uncoalesced loads and stores at the two ends of the launch)
+    //   gid_perm : the arrays themselves have been reordered for the launch (the host gathers them into slot order before
+    //              and scatters them back after, qekf_capi.cu permute_state), so slot j works on row j, coalesced, and
+    //              only the noise identity is perm[j] (the thread-per-filter kernels, single-rate and delayed fusion)
     const int32_t *perm;
+    const int32_t *gid_perm;
 };
 
 // the parameter view of filter i: launch-wide constants, or this filter's column of the override table
@@ -115,7 +121,9 @@ template <typename T, bool SYNTH> struct Inputs {
     double bias[6];
     int32_t priv_start;
 
-    QEKF_FN void init(const RunArgs<T> &a, int64_t i)
+    // i: row of this filter in the per-filter arrays; id: its index in the handle's id space (noise identity)
+    QEKF_FN void init(const RunArgs<T> &a, int64_t i) { init(a, i, i); }
+    QEKF_FN void init(const RunArgs<T> &a, int64_t i, int64_t id)
     {
         imu_i = a.in.imu + i * a.in.is;
         tag_i = a.in.tag_pose + i * a.in.is;
@@ -123,7 +131,7 @@ template <typename T, bool SYNTH> struct Inputs {
         valid_i = (!SYNTH && a.in.tag_valid) ? a.in.tag_valid + i : nullptr;
         vs = a.in.vs;
         ns = &a.ns;
-        gid = a.ns.gid0 + i;
+        gid = a.ns.gid0 + id;
         if (SYNTH) {
             true_bias(a.ns, gid, bias);
             priv_start = private_dropout_start(a.ns, gid);
@@ -479,7 +487,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
         upds = a.st.upds[i];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
-        in.init(a, i);
+        in.init(a, i, a.st.gid_perm ? (int64_t)a.st.gid_perm[i] : i);
         k = (int32_t)a.k0;
         if (SYNTH) {                   // the true bias as its six normals, in the scratch
             float z[6];
@@ -724,7 +732,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
         nh = a.st.nh[i]; hpos = a.st.hpos[i]; hlen = a.st.hlen[i];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
-        in.init(a, i);
+        in.init(a, i, a.st.gid_perm ? (int64_t)a.st.gid_perm[i] : i);
         k = (int32_t)a.k0;
         if (SYNTH) {                   // the true bias as its six normals, in the scratch (12 registers less across calls)
             float z[6];
@@ -930,7 +938,7 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int64_t slot = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = slot < a.st.n;
-    const int64_t i = (live && a.st.perm) ? (int64_t)a.st.perm[slot] : slot;
+    const int64_t i = slot;      // (a reordered launch has its arrays in slot order: DeviceState::gid_perm)
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
     // padding lanes still take part in the votes
@@ -1020,18 +1028,33 @@ __global__ void __launch_bounds__(TICK_BLOCK) tick_kernel(const __grid_constant_
     if (live && tag_mode != 0) deliver_one<T, BIAS, false>(a.st, a.c, pose8, 0, 0, tag_mode == 1, P, i);
     if (MR) run_filter_mr<T, BIAS, DIRECT, false, false>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, TICK_BLOCK, live, vbuf);
     else run_filter<T, BIAS, DIRECT, false, false>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, TICK_BLOCK, live, vbuf);
-    if (live && i < n_out) {
-        const DeviceState<T> &st = a.st;
-        double *r = out + i * TICK_REC;
-        for (int e = 0; e < 16; ++e) r[e] = (double)st.x[e * st.ld + i];
-        for (int p = 0; p < N; ++p)
-            for (int q2 = 0; q2 < N; ++q2) r[16 + p * N + q2] = (double)st.P[sym_idx<N>(p, q2) * st.ld + i];
-        for (int e = 0; e < AUX_DIM; ++e) r[16 + 225 + e] = (double)st.aux[e * st.ld + i];
-        const int32_t f = st.flags[i];
-        double *fl = r + 16 + 225 + AUX_DIM;
-        fl[0] = (f & FLAG_INIT) ? 1 : 0; fl[1] = (f & FLAG_READY) ? 1 : 0; fl[2] = (f & FLAG_CORRECTED) ? 1 : 0;
-        fl[3] = (f & FLAG_ACTIVE) ? 1 : 0; fl[4] = st.upds[i];
-        fl[5] = (f & FLAG_INIT) ? (st.hlen ? st.hlen[i] : 1) : 0;
+    // the records of this CTA's filters, written by all 32 lanes together (element e of a record by lane e % 32): the
+    // output lives in mapped host memory, and 258 single-lane stores would cross PCIe as 258 transactions
+    __syncwarp();
+    __threadfence_block();
+    const DeviceState<T> &st = a.st;
+    const int64_t f0 = (int64_t)blockIdx.x * TICK_BLOCK;
+    for (int64_t f = f0; f < f0 + TICK_BLOCK && f < st.n && f < n_out; ++f) {
+        double *r = out + f * TICK_REC;
+        const int32_t fl = st.flags[f];
+        for (int e = threadIdx.x; e < TICK_REC; e += TICK_BLOCK) {
+            double v = 0.0;
+            if (e < 16) v = (double)st.x[e * st.ld + f];
+            else if (e < 16 + 225) {
+                const int idx = e - 16, p = idx / N, q2 = idx - p * N;
+                if (p < N) v = (double)st.P[sym_idx<N>(p, q2) * st.ld + f];
+            } else if (e < 16 + 225 + AUX_DIM) v = (double)st.aux[(e - 16 - 225) * st.ld + f];
+            else {
+                const int w = e - (16 + 225 + AUX_DIM);
+                if (w == 0) v = (fl & FLAG_INIT) ? 1 : 0;
+                else if (w == 1) v = (fl & FLAG_READY) ? 1 : 0;
+                else if (w == 2) v = (fl & FLAG_CORRECTED) ? 1 : 0;
+                else if (w == 3) v = (fl & FLAG_ACTIVE) ? 1 : 0;
+                else if (w == 4) v = st.upds[f];
+                else v = (fl & FLAG_INIT) ? (st.hlen ? st.hlen[f] : 1) : 0;
+            }
+            r[e] = v;
+        }
     }
 }
 

@@ -61,7 +61,10 @@ QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
     const float r = sqrtf(-2.0f * logf(u1));
     float s, c;
 #ifdef __CUDA_ARCH__
-    sincospif(2.0f * u2, &s, &c);
+    // the SFU's sin / cos (absolute error < 7e-7 on [0, 2 pi): a relative 7e-7 of a noise sample) instead of sincospif's
+    // range reduction and two polynomials: 6 instructions per pair instead of 35, on the per-tick path of every filter
+    s = __sinf(6.2831853071795865f * u2);
+    c = __cosf(6.2831853071795865f * u2);
 #else
     s = (float)::sin(6.283185307179586 * (double)u2);
     c = (float)::cos(6.283185307179586 * (double)u2);

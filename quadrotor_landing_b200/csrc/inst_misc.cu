@@ -100,6 +100,33 @@ cudaError_t launch_stats_reduce(const double *acc, double *out, int64_t n, cudaS
     return cudaGetLastError();
 }
 
+// Reorder the columns of a [rows][ld] array of 4- or 8-byte words.  to_slots: dst[r][j] = src[r][perm[j]] (thread slot j
+// gets filter perm[j]); else the inverse, dst[r][perm[j]] = src[r][j].  Columns n..ld-1 (padding) are copied as they are.
+// One thread per column, blockIdx.y strides over the rows, so perm[j] is read once per thread and the side that is
+// indexed by j is coalesced.
+template <typename W>
+__global__ void permute_rows_kernel(W *__restrict__ dst, const W *__restrict__ src, const int32_t *__restrict__ perm,
+                                    int64_t rows, int64_t ld, int64_t n, int to_slots)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    const int64_t pj = (j < n) ? (int64_t)perm[j] : j;
+    const int64_t sj = to_slots ? pj : j, dj = to_slots ? j : pj;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) dst[r * ld + dj] = src[r * ld + sj];
+}
+
+template <typename W>
+cudaError_t launch_permute_rows(W *dst, const W *src, const int32_t *perm, int64_t rows, int64_t ld, int64_t n, bool to_slots,
+                                cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((ld + 255) / 256), (unsigned)(rows < 64 ? rows : 64));
+    permute_rows_kernel<W><<<grid, 256, 0, stream>>>(dst, src, perm, rows, ld, n, to_slots ? 1 : 0);
+    return cudaGetLastError();
+}
+template cudaError_t launch_permute_rows<uint32_t>(uint32_t *, const uint32_t *, const int32_t *, int64_t, int64_t, int64_t, bool, cudaStream_t);
+template cudaError_t launch_permute_rows<uint64_t>(uint64_t *, const uint64_t *, const int32_t *, int64_t, int64_t, int64_t, bool, cudaStream_t);
+
 template <typename T> __global__ void fma_peak_kernel(T *sink, int iters)
 {
     T a[16];

@@ -43,6 +43,11 @@ template <typename T>
 cudaError_t launch_dump(const RunArgs<T> &a, int64_t first, int64_t count, int64_t T_ticks, double *imu_out,
                         double *tag_out, uint8_t *valid_out, double *bias_out, cudaStream_t stream);
 
+// column reordering of a [rows][ld] array of 4- / 8-byte words (W = uint32_t / uint64_t): filter order <-> slot order
+template <typename W>
+cudaError_t launch_permute_rows(W *dst, const W *src, const int32_t *perm, int64_t rows, int64_t ld, int64_t n, bool to_slots,
+                                cudaStream_t stream);
+
 // independent FMA chains, no memory traffic: `iters` x 16 FMAs per thread
 template <typename T> cudaError_t launch_fma_peak(T *sink, int iters, unsigned grid, unsigned block, cudaStream_t stream);
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -89,11 +90,14 @@ struct qekf_handle {
     // slot -> filter order of the Monte-Carlo replay (filters sorted by the start of their private dropout), and the
     // noise-spec fields it was derived from
     int32_t *d_perm = nullptr;
-    void *stats_save = nullptr;      // [np][ld]: slot-indexed parking space of the statistics sample while d_perm is in use
+    void *perm_scratch = nullptr;    // staging buffer of the reordering passes (as large as the largest per-filter array)
+    size_t perm_scratch_bytes = 0;
+    bool in_slot_order = false;      // the per-filter arrays are currently reordered (only ever true inside qekf_run_monte_carlo)
     uint64_t perm_seed = 0;
     int64_t perm_gid0 = 0;
     int32_t perm_len = 0, perm_lo = 0, perm_hi = 0;
     bool perm_on = true;             // QEKF_NO_PERM=1 disables it (A/B runs)
+    int64_t perm_min_steps = 256;    // shortest replay that is reordered (QEKF_PERM_MIN_STEPS overrides)
     // launch bookkeeping
     int64_t launches = 0;
     // mapping of the fused replay (qekf_set_mapping), where the kernels exist (FP64, single-rate): 2 = two role-specialised
@@ -115,6 +119,7 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     s.pf = h->pf_on ? (const T *)h->pf : nullptr;
     s.pf_delay = h->pf_on ? h->pf_delay : nullptr;
     s.perm = nullptr;
+    s.gid_perm = nullptr;
     return s;
 }
 
@@ -150,8 +155,8 @@ int free_state(qekf_handle *h)
     cudaFree(h->flags); cudaFree(h->upds); cudaFree(h->d_tick); cudaFree(h->d_in);
     cudaFree(h->stats_acc); cudaFree(h->stats_red); cudaFree(h->d_shared); cudaFree(h->counts);
     cudaFree(h->xc); cudaFree(h->Pc); cudaFree(h->ring); cudaFree(h->nh); cudaFree(h->hpos); cudaFree(h->hlen);
-    cudaFree(h->pf); cudaFree(h->pf_delay); cudaFree(h->d_mask); cudaFree(h->d_perm); cudaFree(h->stats_save);
-    h->d_perm = nullptr; h->perm_len = 0; h->stats_save = nullptr;
+    cudaFree(h->pf); cudaFree(h->pf_delay); cudaFree(h->d_mask); cudaFree(h->d_perm); cudaFree(h->perm_scratch);
+    h->d_perm = nullptr; h->perm_len = 0; h->perm_scratch = nullptr; h->perm_scratch_bytes = 0; h->in_slot_order = false;
     h->d_mask = nullptr; h->d_mask_bytes = 0;
     h->xc = h->Pc = h->ring = nullptr; h->nh = h->hpos = h->hlen = nullptr; h->ring_len = 0;
     h->pf = nullptr; h->pf_delay = nullptr; h->pf_on = false;
@@ -280,13 +285,11 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
     a.k0 = k0; a.n_steps = n_steps; a.m0 = m0;
     if (ns) {
         a.ns = *ns;
-        // slot order (qekf_run_monte_carlo keeps it in step with the noise spec; may be null).  Single-rate thread-per-filter
-        // kernels only: the delayed-fusion kernel touches its per-filter IMU ring in HBM every tick, and a permuted
-        // filter index makes those accesses uncoalesced (measured: 3.5e9 -> 1.6e9 filter-steps/s)
-        const bool tpf = h->lanes_per_filter == 1 || h->precision != QEKF_FP64;
-        a.st.perm = (tpf && !h->p.multirate_ekf) ? h->d_perm : nullptr;
+        // a reordered launch (qekf_run_monte_carlo has gathered the per-filter arrays into slot order): row j of every
+        // array belongs to filter d_perm[j], which is what keys its noise
+        a.st.gid_perm = h->in_slot_order ? h->d_perm : nullptr;
         if (h->stats_acc && truth && h->stats_stride > 0) {
-            a.stats.save = a.st.perm ? h->stats_save : nullptr;
+            a.stats.save = nullptr;
             a.stats.acc = h->stats_acc; a.stats.truth = truth;
             a.stats.n_bins = h->stats_bins; a.stats.stride = h->stats_stride;
             // two-sided 95% chi-square interval for n degrees of freedom
@@ -408,10 +411,47 @@ int ensure_perm(qekf_handle *h, const NoiseSpec &ns)
     h->perm_seed = ns.seed; h->perm_gid0 = ns.gid0; h->perm_len = ns.rdrop_len; h->perm_lo = ns.rdrop_lo; h->perm_hi = ns.rdrop_hi;
     return QEKF_OK;
 }
-int ensure_stats_save(qekf_handle *h)
+// Reorder every per-filter array of the handle between filter order (row i = filter i: what every accessor and every
+// other entry point assumes) and slot order (row j = filter d_perm[j]: what a reordered Monte-Carlo launch works on).
+// Each array is gathered into the staging buffer and copied back: two streaming passes over the state per direction
+// (~3 ms per million delayed-fusion filters), against seconds of replay.
+int permute_state(qekf_handle *h, bool to_slots)
 {
-    if (h->d_perm && h->stats_acc && !h->stats_save)
-        CUDA_TRY(cudaMalloc(&h->stats_save, (size_t)h->np * (size_t)h->ld * h->tsize));
+    if (h->in_slot_order == to_slots || !h->d_perm) return QEKF_OK;
+    struct Arr { void *p; int64_t rows; size_t word; };
+    const int64_t ld = h->ld;
+    std::vector<Arr> arrs = { { h->x, 16, h->tsize }, { h->P, h->np, h->tsize }, { h->aux, AUX_DIM, h->tsize },
+                              { h->pend, PEND_DIM, 8 }, { h->flags, 1, 4 }, { h->upds, 1, 4 } };
+    if (h->xc) {
+        arrs.push_back({ h->xc, 16, h->tsize });
+        arrs.push_back({ h->Pc, h->np, h->tsize });
+        arrs.push_back({ h->ring, (int64_t)h->ring_len * 6, h->tsize });
+        arrs.push_back({ h->nh, 1, 4 });
+        arrs.push_back({ h->hpos, 1, 4 });
+        arrs.push_back({ h->hlen, 1, 4 });
+    }
+    if (h->pf_on) {
+        arrs.push_back({ h->pf, PF_DIM, h->tsize });
+        arrs.push_back({ h->pf_delay, 2, 8 });
+    }
+    size_t need = 0;
+    for (const Arr &a : arrs) need = std::max(need, (size_t)a.rows * (size_t)ld * a.word);
+    if (need > h->perm_scratch_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->perm_scratch);
+        h->perm_scratch = nullptr; h->perm_scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->perm_scratch, need));
+        h->perm_scratch_bytes = need;
+    }
+    for (const Arr &a : arrs) {
+        if (a.word == 8)
+            CUDA_TRY(launch_permute_rows<uint64_t>((uint64_t *)h->perm_scratch, (const uint64_t *)a.p, h->d_perm, a.rows, ld, h->n, to_slots, h->stream));
+        else
+            CUDA_TRY(launch_permute_rows<uint32_t>((uint32_t *)h->perm_scratch, (const uint32_t *)a.p, h->d_perm, a.rows, ld, h->n, to_slots, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(a.p, h->perm_scratch, (size_t)a.rows * (size_t)ld * a.word, cudaMemcpyDeviceToDevice, h->stream));
+        h->launches++;
+    }
+    h->in_slot_order = to_slots;
     return QEKF_OK;
 }
 
@@ -596,6 +636,8 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
         if (e && coop_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->coop_groups = atoi(e);
         e = getenv("QEKF_NO_PERM");
         if (e && atoi(e) != 0) h->perm_on = false;
+        e = getenv("QEKF_PERM_MIN_STEPS");
+        if (e && atoll(e) > 0) h->perm_min_steps = atoll(e);
         e = getenv("QEKF_DUO_GROUPS");
         if (e && duo_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->duo_groups = atoi(e);
     }
@@ -1316,9 +1358,20 @@ int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qek
     NoiseSpec ns = to_device_noise(*n);
     rc = ensure_perm(h, ns);
     if (rc) return rc;
-    rc = ensure_stats_save(h);
-    if (rc) return rc;
-    return run_dispatch(h, in, k0, n_steps, m0, &ns, truth);
+    // Long replays of the thread-per-filter kernels run on reordered arrays (filters that share a CTA share the phase of
+    // their private dropout); a short one (a trace chunk, a test) would not repay the two reordering passes
+    const bool tpf = h->lanes_per_filter == 1 || h->precision != QEKF_FP64 || h->p.multirate_ekf;
+    const bool reorder = h->d_perm && tpf && n_steps >= h->perm_min_steps;
+    if (reorder) {
+        rc = permute_state(h, true);
+        if (rc) return rc;
+    }
+    rc = run_dispatch(h, in, k0, n_steps, m0, &ns, truth);
+    if (reorder) {
+        const int rc2 = permute_state(h, false);
+        if (!rc) rc = rc2;
+    }
+    return rc;
 }
 
 int qekf_synthesize_streams(qekf_handle *h, const qekf_shared_streams *s, const qekf_noise_spec *n, int64_t first,

@@ -1,0 +1,78 @@
+"""Stall samples of an `ncu --page source --csv --print-source cuda,sass` export by code region and stall reason.
+Usage: ncu_regions.py export.csv warp_ticks"""
+import csv
+import sys
+from collections import Counter, defaultdict
+
+rows = list(csv.reader(open(sys.argv[1])))
+div = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+
+
+def region(f, l):
+    if f == "ekf_core.cuh":
+        for hi, name in ((60, "core:scalar wrappers (fma/sqrt..)"), (240, "core:P ld/st + 3x3 helpers"), (402, "core:quat/attitude"),
+                         (437, "core:init_state"), (501, "core:pred_nominal"), (669, "core:pred_cov"), (740, "core:sym6inv"),
+                         (845, "core:corr_front"), (1052, "core:correction")):
+            if l <= hi:
+                return name
+        return "core:gate"
+    if f == "ekf_synth.cuh":
+        return "synth:nees" if l >= 215 else "synth:noise"
+    if f == "ekf_kernels.cuh":
+        for hi, name in ((187, "k:inputs"), (279, "k:stats_sample"), (317, "k:load/store filter"), (335, "k:correction_call"),
+                         (417, "k:votes"), (445, "k:SmemInt"), (620, "k:run_filter (single rate)"), (665, "k:checkpoint/advance_call"),
+                         (905, "k:run_filter_mr")):
+            if l <= hi:
+                return name
+        return "k:other"
+    return f
+
+
+fname = hdr = cur = st = None
+reg = defaultdict(Counter)
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        fname = r[1].split("/")[-1]
+        continue
+    if r[0] == "Line No":
+        hdr = r
+        ix = {h: i for i, h in enumerate(hdr)}
+        st = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+        continue
+    if hdr is None:
+        continue
+    if r[0] != "":
+        try:
+            cur = (fname, int(r[0]))
+        except ValueError:
+            cur = None
+        continue
+    if cur is None or len(r) < len(hdr):
+        continue
+    g = region(*cur)
+    try:
+        reg[g]["instr"] += float(r[ix["Instructions Executed"]] or 0)
+        for h in st:
+            reg[g][h] += float(r[ix[h]] or 0)
+        if "LDL" in r[3] or "STL" in r[3]:
+            reg[g]["local"] += float(r[ix["Instructions Executed"]] or 0)
+    except (ValueError, IndexError):
+        pass
+tot = sum(sum(v[h] for h in st) for v in reg.values())
+cols = ["stall_wait", "stall_long_sb", "stall_selected", "stall_barrier", "stall_math", "stall_short_sb", "stall_not_selected", "stall_no_inst", "stall_lg"]
+print("(per-line attribution: inlined code is counted at every line of its inline stack, so instruction columns overlap)")
+print("%-36s %8s %7s %6s | %s other" % ("region", "instr/u", "local/u", "stall%", " ".join(c[6:11].rjust(5) for c in cols)))
+for g, v in sorted(reg.items(), key=lambda kv: -sum(kv[1][h] for h in st)):
+    s = sum(v[h] for h in st)
+    if s < tot * 0.003:
+        continue
+    f = [100 * v[h] / tot for h in cols]
+    print("%-36s %8.1f %7.1f %5.1f%% | %s %5.1f" % (g, v["instr"] / div, v["local"] / div, 100 * s / tot, " ".join("%5.1f" % x for x in f),
+                                                  100 * s / tot - sum(f)))
+allc = Counter()
+for v in reg.values():
+    for h in st:
+        allc[h] += v[h]
+print("total by reason: " + ", ".join("%s %.1f%%" % (h[6:], 100 * n / tot) for h, n in allc.most_common(10)))
