@@ -1106,13 +1106,13 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
         bool init_now = false;
         if (active && k == next_tag_step) {
-            if (in.valid(a.in, m, (int32_t)k)) {
+            if (in.valid(a.in, a.ns, m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     if (lead) {        // initialize_state (cpp:305-344): the nominal part, in role 0's (= the global) frame
                         T tg[7];
-                        in.tag(a.in, m, tg);
+                        in.tag(a.in, a.ns, m, tg);
                         PNull<T, 3 * NB> pn;
                         initialize_state<T, BIAS>(s, pn, tg, rp, false);   // role 0's parameter view is not relabelled
                     }
@@ -1158,7 +1158,7 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
         if (exec && want) {
             T tg[7];
             if (pend_m >= 0) {
-                in.tag(a.in, pend_m, tg);
+                in.tag(a.in, a.ns, pend_m, tg);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < 7; ++cc) tg[cc] = (T)a.st.pend[cc * a.st.ld + i];
@@ -1243,7 +1243,7 @@ QEKF_FN void run_filter_coop(const RunArgs<T> &a, const int64_t i_in, PL &P, con
 
     if (lead && (flags & FLAG_READY) && pend_m >= 0) {
         double tg[7];
-        in.tag_f64(a.in, pend_m, tg);
+        in.tag_f64(a.in, a.ns, pend_m, tg);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];

@@ -313,7 +313,7 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
         double raw[6];
         T u[6];
         in.raw_imu(a.in, kk, raw);
-        in.imu(kk, raw, u);
+        in.imu(a.ns, kk, raw, u);
         kin_publish(s, accel, u, c, X);
     };
 
@@ -323,13 +323,13 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
         if (active && k == next_tag_step) {
-            if (in.valid(a.in, m, (int32_t)k)) {
+            if (in.valid(a.in, a.ns, m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {       // initialize_state (cpp:305-344): nominal part by B, covariance by A
                     if (rb) {
                         T tg[7];
-                        in.tag(a.in, m, tg);
+                        in.tag(a.in, a.ns, m, tg);
                         PNull<T, PS::n> pn;
                         initialize_state<T, BIAS>(s, pn, tg, par, false);
                     } else {
@@ -378,7 +378,7 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
         T tag[7];
         if (exec && want) {
             if (pend_m >= 0) {
-                in.tag(a.in, pend_m, tag);
+                in.tag(a.in, a.ns, pend_m, tag);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
@@ -472,7 +472,7 @@ QEKF_FN void run_filter_duo(const RunArgs<T> &a, const int64_t i_in, PS &P, cons
     } else {
         if ((flags & FLAG_READY) && pend_m >= 0) {
             double tg[7];
-            in.tag_f64(a.in, pend_m, tg);
+            in.tag_f64(a.in, a.ns, pend_m, tg);
 #pragma unroll
             for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * ld + i] = tg[cc];
             a.st.pend[7 * ld + i] = a.in.tag_stamp[pend_m];

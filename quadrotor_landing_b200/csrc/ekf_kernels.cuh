@@ -116,7 +116,6 @@ template <typename T, bool SYNTH> struct Inputs {
     int64_t cs;
     const uint8_t *valid_i;
     int64_t vs;
-    const NoiseSpec *ns;
     int64_t gid;
     double bias[6];
     int32_t priv_start;
@@ -130,7 +129,6 @@ template <typename T, bool SYNTH> struct Inputs {
         cs = a.in.cs;
         valid_i = (!SYNTH && a.in.tag_valid) ? a.in.tag_valid + i : nullptr;
         vs = a.in.vs;
-        ns = &a.ns;
         gid = a.ns.gid0 + id;
         if (SYNTH) {
             true_bias(a.ns, gid, bias);
@@ -147,12 +145,12 @@ template <typename T, bool SYNTH> struct Inputs {
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) u[cc] = SYNTH ? sv.imu[k * 6 + cc] : imu_i[(k * 6 + cc) * cs];
     }
-    // turn the raw (prefetched) sample of tick k into what the filter sees
-    QEKF_FN void imu(int64_t k, const double raw[6], T u[6]) const
+    // turn the raw sample of tick k into what the filter sees
+    QEKF_FN void imu(const NoiseSpec &ns, int64_t k, const double raw[6], T u[6]) const
     {
         if (SYNTH) {
             double un[6];
-            synth_imu(*ns, gid, k, raw, bias, un);
+            synth_imu(ns, gid, k, raw, bias, un);
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) u[cc] = (T)un[cc];
         } else {
@@ -160,9 +158,10 @@ template <typename T, bool SYNTH> struct Inputs {
             for (int cc = 0; cc < 6; ++cc) u[cc] = (T)raw[cc];
         }
     }
-    // `sv` is the launch's StreamView (kernel-parameter resident): the front-end's shared arrays are read through
-    // it rather than through per-lane copies of the pointers
-    QEKF_FN void tag_f64(const StreamView &sv, int32_t m, double tag[7]) const
+    // `sv`, `ns`: the launch's StreamView and NoiseSpec (kernel-parameter resident, passed by the caller as a.in, a.ns):
+    // read through the constant bank rather than through per-lane copies of pointers, which would live in local memory
+    // and turn every access into a generic load
+    QEKF_FN void tag_f64(const StreamView &sv, const NoiseSpec &ns, int32_t m, double tag[7]) const
     {
         double raw[7];
         // SYNTH launches read the one shared clean scenario (element stride 1) straight through the kernel
@@ -170,26 +169,31 @@ template <typename T, bool SYNTH> struct Inputs {
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) raw[cc] = SYNTH ? sv.tag_pose[(int64_t)m * 7 + cc] : tag_i[((int64_t)m * 7 + cc) * cs];
         if (SYNTH) {
-            double sp = (double)ns->sig_p, sth = (double)ns->sig_th;
+            double sp = (double)ns.sig_p, sth = (double)ns.sig_th;
             if (sv.tag_sigma) { sp = sv.tag_sigma[2 * m]; sth = sv.tag_sigma[2 * m + 1]; }
-            synth_tag(*ns, gid, m, raw, tag, sp, sth);
+            synth_tag(ns, gid, m, raw, tag, sp, sth);
         }
         else {
 #pragma unroll
             for (int cc = 0; cc < 7; ++cc) tag[cc] = raw[cc];
         }
     }
-    QEKF_FN void tag(const StreamView &sv, int32_t m, T t[7]) const
+    QEKF_FN void tag(const StreamView &sv, const NoiseSpec &ns, int32_t m, T t[7]) const
     {
         double d[7];
-        tag_f64(sv, m, d);
+        tag_f64(sv, ns, m, d);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) t[cc] = (T)d[cc];
     }
-    QEKF_FN bool valid(const StreamView &sv, int32_t m, int32_t step) const
+    QEKF_FN bool valid(const StreamView &sv, const NoiseSpec &ns, int32_t m, int32_t step) const
+    {
+        return valid(sv, ns, m, step, priv_start);
+    }
+    // (pstart: this filter's private_dropout_start, kept by the caller where it pleases)
+    QEKF_FN bool valid(const StreamView &sv, const NoiseSpec &ns, int32_t m, int32_t step, int32_t pstart) const
     {
         // SYNTH: sv.tag_valid is the detection front-end's visibility mask [M], shared by all filters (or nullptr)
-        if (SYNTH) return arrival_valid(*ns, step, priv_start) && (sv.tag_valid == nullptr || sv.tag_valid[m] != 0);
+        if (SYNTH) return arrival_valid(ns, step, pstart) && (sv.tag_valid == nullptr || sv.tag_valid[m] != 0);
         return valid_i ? (valid_i[(int64_t)m * vs] != 0) : true;
     }
 };
@@ -443,9 +447,10 @@ struct SmemInt {
     QEKF_FN SmemInt &operator++() { *p += 1; return *this; }
 };
 // per-lane scratch words of the replay loops:
-//   delayed fusion: flags upds nh hpos hlen m next_tag_step pend_m held k | 6 floats: the true bias' normals
+//   delayed fusion: flags upds nh hpos hlen m next_tag_step pend_m held k | 6 floats: the true bias' normals | n_pred
+//                   priv_start
 //   single rate   : flags upds n_pred n_corr n_iter m next_tag_step pend_m held k | 6 floats: the true bias' normals
-constexpr int MR_SCRATCH_INTS = 16;
+constexpr int MR_SCRATCH_INTS = 18;
 constexpr int SR_SCRATCH_INTS = 16;
 
 // The per-filter replay loop, one lane per filter.  Host-callable so that the CPU-side unit tests
@@ -465,11 +470,15 @@ constexpr int SR_SCRATCH_INTS = 16;
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
 QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
-                        const bool live = true, int *vbuf = nullptr)
+                        const bool live = true, int *vbuf = nullptr, const Consts<T> *c_cold = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
     const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
+    // what the out-of-line calls read the launch-wide constants through: a reference to kernel parameters turns into
+    // generic loads from their global-memory image once it crosses a call (L2 latency with this kernel's squeezed L1);
+    // the kernels therefore hand over a shared-memory copy
+    const typename ParSel<T, PF>::type par_cold = ParSel<T, PF>::make(c_cold ? *c_cold : a.c, a.st, i);
     const int32_t k_end = (int32_t)(a.k0 + a.n_steps);       // (qekf_run bounds tick indices to 31 bits)
     Nominal<T> s;
     SmemInt flags{ scr + 0 * scr_stride }, upds{ scr + 1 * scr_stride }, n_pred{ scr + 2 * scr_stride };
@@ -519,12 +528,12 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176); idempotent ----
         if (active && k == next_tag_step) {
-            if (in.valid(a.in, m, (int32_t)k)) {
+            if (in.valid(a.in, a.ns, m, (int32_t)k)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     T tag0[7];
-                    in.tag(a.in, m, tag0);
+                    in.tag(a.in, a.ns, m, tag0);
                     initialize_state<T, BIAS>(s, P, tag0, par, false);
                     flags |= FLAG_INIT;
                 }
@@ -559,7 +568,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
         T tag[7];
         if (exec && want) {
             if (pend_m >= 0) {
-                in.tag(a.in, pend_m, tag);
+                in.tag(a.in, a.ns, pend_m, tag);
             } else {
 #pragma unroll
                 for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
@@ -585,7 +594,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
 #pragma unroll
                 for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
             } else {
-                in.imu(k, un, u);
+                in.imu(a.ns, k, un, u);
             }
             prediction_step<T, BIAS>(s, P, u, par, accel);
             ++n_pred;
@@ -594,7 +603,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
                 Observation<T> obs;
                 {
                     Nominal<T> tmp = s;
-                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, par, &obs);
+                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, par_cold, &obs);
                     s = tmp;
                 }
 #pragma unroll
@@ -620,7 +629,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
     // a latched, still unconsumed measurement survives the launch in st.pend
     if ((flags & FLAG_READY) && pend_m >= 0) {
         double tg[7];
-        in.tag_f64(a.in, pend_m, tg);
+        in.tag_f64(a.in, a.ns, pend_m, tg);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
@@ -708,11 +717,12 @@ QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_
 // events, where the warp executes prediction code anyway.
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
 QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
-                           const bool live = true, int *vbuf = nullptr)
+                           const bool live = true, int *vbuf = nullptr, const Consts<T> *c_cold = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
     const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
+    const typename ParSel<T, PF>::type par_cold = ParSel<T, PF>::make(c_cold ? *c_cold : a.c, a.st, i);   // see run_filter
     const int64_t k_end = a.k0 + a.n_steps;
     const int32_t L = a.st.ring_len, Dm1 = a.st.dmax_m1;
     T *ring_i = a.st.ring + i;
@@ -721,7 +731,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
     SmemInt hpos{ scr + 3 * scr_stride }, hlen{ scr + 4 * scr_stride }, m{ scr + 5 * scr_stride };
     SmemInt next_tag_step{ scr + 6 * scr_stride }, pend_m{ scr + 7 * scr_stride }, held{ scr + 8 * scr_stride };
     SmemInt k{ scr + 9 * scr_stride };       // tick index (qekf_run bounds it to int32)
-    flags = 0; upds = 0; nh = 0; hpos = 0; hlen = 0;
+    SmemInt n_pred{ scr + 16 * scr_stride }, pstart{ scr + 17 * scr_stride };
+    flags = 0; upds = 0; nh = 0; hpos = 0; hlen = 0; n_pred = 0; pstart = INT32_MAX;
     T accel[3] = { T(0), T(0), T(0) };
     Inputs<T, SYNTH> in;
     k = (int32_t)k_end;
@@ -734,6 +745,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
         for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
         in.init(a, i, a.st.gid_perm ? (int64_t)a.st.gid_perm[i] : i);
         k = (int32_t)a.k0;
+        if (SYNTH) pstart = in.priv_start;
         if (SYNTH) {                   // the true bias as its six normals, in the scratch (12 registers less across calls)
             float z[6];
             normals6(a.ns, in.gid, STREAM_BIAS, 0u, z);
@@ -747,7 +759,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
             b[cc] = (double)(cc < 3 ? a.ns.sig_ba : a.ns.sig_bw) * (double)reinterpret_cast<const float *>(scr)[(10 + cc) * scr_stride];
     };
 
-    uint32_t n_pred = 0, n_corr = 0, n_iter = 0, n_sexec = 0;
+    uint32_t n_corr = 0, n_iter = 0, n_sexec = 0;
     m = a.m0;
     next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     pend_m = -1;
@@ -762,12 +774,12 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 
         // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176) ----
         if (active && k == next_tag_step) {
-            if (in.valid(a.in, m, (int32_t)k)) {
+            if (in.valid(a.in, a.ns, m, (int32_t)k, pstart)) {
                 pend_m = m;
                 flags |= FLAG_READY;
                 if (!(flags & FLAG_INIT)) {
                     T tag0[7];
-                    in.tag(a.in, m, tag0);
+                    in.tag(a.in, a.ns, m, tag0);
                     initialize_state<T, BIAS>(s, P, tag0, par, false);
                     flags |= FLAG_INIT;
                     nh = 0; hlen = 1;                    // history <- single entry (cpp:326-339)
@@ -790,8 +802,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
                 store_checkpoint<T>(a.st, i, s, P);
                 int32_t first = hpos - nh + 1;
                 if (first < 0) first += L;
-                advance_call<T, BIAS>(&head, P, par, ring_i, a.st.ld, L, first, nh, accel);
-                n_pred += (uint32_t)nh;
+                advance_call<T, BIAS>(&head, P, par_cold, ring_i, a.st.ld, L, first, nh, accel);
+                n_pred += nh;
             }
             double tb[6] = { 0, 0, 0, 0, 0, 0 };
             if (SYNTH) true_bias_now(tb);
@@ -814,7 +826,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
         double stamp = 0;
         if (exec && want) {
             if (pend_m >= 0) {
-                in.tag(a.in, pend_m, tag);
+                in.tag(a.in, a.ns, pend_m, tag);
                 stamp = a.in.tag_stamp[pend_m];
             } else {
 #pragma unroll
@@ -847,14 +859,14 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
             int32_t first = hpos - nh + 1;
             if (first < 0) first += L;
             T scratch[3] = { T(0), T(0), T(0) };
-            advance_call<T, BIAS>(&s, P, par, ring_i, a.st.ld, L, first, n_adv, scratch);
+            advance_call<T, BIAS>(&s, P, par_cold, ring_i, a.st.ld, L, first, n_adv, scratch);
             nh -= n_adv;
-            n_pred += (uint32_t)n_adv;
+            n_pred += n_adv;
         }
         if (perform) {
             ++n_corr;
             Observation<T> obs;
-            correction_call<T, BIAS, DIRECT>(&s, P, tag, par, &obs);
+            correction_call<T, BIAS, DIRECT>(&s, P, tag, par_cold, &obs);
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
@@ -876,7 +888,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 #pragma unroll
                     for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
                 } else {
-                    in.imu(k, un, u);
+                    in.imu(a.ns, k, un, u);
                 }
             }
             hpos = (hpos + 1 == L) ? 0 : hpos + 1;
@@ -896,7 +908,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
 
     if ((flags & FLAG_READY) && pend_m >= 0) {
         double tg[7];
-        in.tag_f64(a.in, pend_m, tg);
+        in.tag_f64(a.in, a.ns, pend_m, tg);
 #pragma unroll
         for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
         a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
@@ -907,8 +919,8 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
         store_checkpoint<T>(a.st, i, s, P);
         int32_t first = hpos - nh + 1;
         if (first < 0) first += L;
-        advance_call<T, BIAS>(&s, P, par, ring_i, a.st.ld, L, first, nh, accel);
-        n_pred += (uint32_t)nh;
+        advance_call<T, BIAS>(&s, P, par_cold, ring_i, a.st.ld, L, first, nh, accel);
+        n_pred += nh;
         store_filter<T>(a.st, i, s, P);
     }
     a.st.flags[i] = flags;
@@ -916,18 +928,31 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
     a.st.nh[i] = nh; a.st.hpos[i] = hpos; a.st.hlen[i] = hlen;
     if (a.st.counts) {
 #ifdef __CUDA_ARCH__
-        atomicAdd(a.st.counts + 0, (unsigned long long)n_pred);
+        atomicAdd(a.st.counts + 0, (unsigned long long)(uint32_t)(int32_t)n_pred);
         atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
         if ((i & 31) == 0) atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);
         atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
 #else
-        a.st.counts[0] += n_pred;
+        a.st.counts[0] += (uint32_t)(int32_t)n_pred;
         a.st.counts[1] += n_corr;
 #endif
     }
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
 }
+
+// CTA-cooperative copy of the launch-wide constants into shared memory (whole 8-byte words; VOTE_WORDS and the
+// scratch sizes keep the destination 8-byte aligned)
+template <typename T> __device__ __forceinline__ void copy_consts(Consts<T> *dst, const Consts<T> &src)
+{
+#ifdef __CUDA_ARCH__
+    static_assert(sizeof(Consts<T>) % 8 == 0, "Consts is copied in 8-byte words");
+    const unsigned long long *s = reinterpret_cast<const unsigned long long *>(&src);
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(dst);
+    for (unsigned w = threadIdx.x; w < sizeof(Consts<T>) / 8; w += blockDim.x) d[w] = s[w];
+#endif
+}
+constexpr size_t consts_smem_bytes(size_t consts_size) { return (consts_size + 15) / 16 * 16; }
 
 // fused multi-tick replay: MR = false single-rate filter, MR = true delayed-measurement fusion
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF, int BLOCK>
@@ -941,13 +966,13 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     const int64_t i = slot;      // (a reordered launch has its arrays in slot order: DeviceState::gid_perm)
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
+    // behind the vote words: the sequencer's integers, then a copy of the launch-wide constants for the out-of-line calls
+    int32_t *scr = vbuf + VOTE_WORDS;
+    Consts<T> *csm = reinterpret_cast<Consts<T> *>(scr + (size_t)BLOCK * (MR ? MR_SCRATCH_INTS : SR_SCRATCH_INTS));
+    copy_consts(csm, a.c);             // (published by the barrier of cta_vote_init)
     // padding lanes still take part in the votes
-    if (MR) {
-        // the sequencer's integers live in the shared memory behind the vote words
-        run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, live, vbuf);
-    } else {
-        run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, vbuf + VOTE_WORDS + threadIdx.x, BLOCK, live, vbuf);
-    }
+    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1127,9 +1152,9 @@ __global__ void synth_dump_kernel(RunArgs<T> a, int64_t first, int64_t count, in
     }
     for (int32_t m = 0; m < a.in.M; ++m) {
         double tg[7];
-        in.tag_f64(a.in, m, tg);
+        in.tag_f64(a.in, a.ns, m, tg);
         for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
-        valid_out[(int64_t)m * count + j] = in.valid(a.in, m, a.in.tag_step[m]) ? 1 : 0;
+        valid_out[(int64_t)m * count + j] = in.valid(a.in, a.ns, m, a.in.tag_step[m]) ? 1 : 0;
     }
 }
 

@@ -128,6 +128,7 @@ size_t smem_bytes(const qekf_handle *h)
 {
     size_t b = (size_t)block_of(h) * h->np * h->tsize + VOTE_WORDS * sizeof(int);
     b += (size_t)block_of(h) * (h->p.multirate_ekf ? MR_SCRATCH_INTS : SR_SCRATCH_INTS) * sizeof(int32_t);
+    b += consts_smem_bytes(h->precision == QEKF_FP64 ? sizeof(Consts<double>) : sizeof(Consts<float>));
     return b;
 }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + block_of(h) - 1) / block_of(h)); }

@@ -394,9 +394,9 @@ void hc_synthesize(const qekf_params *p, const qekf_noise_spec *n, int64_t T, co
         }
         for (int32_t m = 0; m < M; ++m) {
             double tg[7];
-            in.tag_f64(a.in, m, tg);
+            in.tag_f64(a.in, a.ns, m, tg);
             for (int c = 0; c < 7; ++c) tag_out[((int64_t)m * 7 + c) * count + j] = tg[c];
-            valid_out[(int64_t)m * count + j] = in.valid(a.in, m, tag_step[m]) ? 1 : 0;
+            valid_out[(int64_t)m * count + j] = in.valid(a.in, a.ns, m, tag_step[m]) ? 1 : 0;
         }
     }
 }
