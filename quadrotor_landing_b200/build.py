@@ -23,6 +23,7 @@ HEADERS = ["ekf_core.cuh", "ekf_synth.cuh", "ekf_kernels.cuh", "ekf_params.hpp",
            "launch_coop.hpp", os.path.join("..", "..", "include", "qekf.h")]
 COOP_HEADERS = ["ekf_coop.cuh", "ekf_duo.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS += os.environ.get("QEKF_NVCC_EXTRA", "").split()     # experiments only (e.g. -DQEKF_EXP8)
 
 
 def _units():

@@ -147,13 +147,18 @@ template <int N> __host__ __device__ constexpr int sym_idx(int i, int j)
 
 // covariance in shared memory, element-major: element e of the filter of lane l at base[e*STRIDE]
 // (base already points at the lane) -> conflict-free 8-byte accesses across a warp.
+#ifdef QEKF_EXP8
+#define QEKF_EXP8_MAP(e) ((sizeof(T) == 8 && N == 15 && (e) >= 105) ? (e) - 15 : (e))
+#else
+#define QEKF_EXP8_MAP(e) (e)
+#endif
 template <typename T, int N, int STRIDE> struct PShared {
     T *base;
     static constexpr int n = N;
-    QEKF_FN T ld(int i, int j) const { return base[sym_idx<N>(i, j) * STRIDE]; }
-    QEKF_FN void st(int i, int j, T v) { base[sym_idx<N>(i, j) * STRIDE] = v; }
-    QEKF_FN T &el(int e) { return base[e * STRIDE]; }
-    QEKF_FN const T &el(int e) const { return base[e * STRIDE]; }
+    QEKF_FN T ld(int i, int j) const { return base[QEKF_EXP8_MAP(sym_idx<N>(i, j)) * STRIDE]; }
+    QEKF_FN void st(int i, int j, T v) { base[QEKF_EXP8_MAP(sym_idx<N>(i, j)) * STRIDE] = v; }
+    QEKF_FN T &el(int e) { return base[QEKF_EXP8_MAP(e) * STRIDE]; }
+    QEKF_FN const T &el(int e) const { return base[QEKF_EXP8_MAP(e) * STRIDE]; }
 };
 
 // covariance in a thread-local array (registers when indices are static)

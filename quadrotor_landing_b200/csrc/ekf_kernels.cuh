@@ -521,6 +521,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
     bool at_fence = false;             // finished a sampling tick; waiting for the warp to catch up
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
+    // the next sampling boundary (a multiple of the stride): every lane of the CTA stops there until all have arrived, so
+    // it is the same for all of them and moves on when the sample is taken -- no k % stride on the per-tick path
+    int32_t next_fence = do_stats ? (int32_t)((a.k0 / a.stats.stride + 1) * a.stats.stride) : INT32_MAX;
 
     cta_vote_init(vbuf);
     for (uint32_t iter = 0;; ++iter) {
@@ -557,6 +560,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
             stats_sample<T, BIAS>(a, i, (int64_t)k - 1, s, P, tb, mine);
             if (mine) ++n_sexec;
             at_fence = false;
+            next_fence += a.stats.stride;
         }
         bool serve = true;
         if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
@@ -621,7 +625,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
         if (active && !(want && !serve)) {
             ++k;
             if (!SYNTH && k < k_end) in.raw_imu(k, un);
-            if (do_stats && (k % a.stats.stride) == 0) at_fence = true;   // tick k-1 was a sampling tick
+            if (k == next_fence) at_fence = true;        // tick k-1 was a sampling tick
         }
     }
     if (!live) return;
@@ -674,6 +678,7 @@ QEKF_FN void store_checkpoint(const DeviceState<T> &st, int64_t i, const Nominal
 }
 
 // n consecutive prediction_steps through the stored IMU inputs of ring slots first, first+1, ... (mod L).
+// (Streaming loads / stores, __ldcs / __stcs, for the ring were measured and cost 8 %: 4.17e9 -> 3.86e9 filter-steps/s.)
 // One out-of-line copy of the prediction code serves the replay before a delayed correction, the checkpoint
 // catch-up and the materialisation of the head, so the whole multirate tick loop stays small.
 template <typename T, bool BIAS, class PS, class PAR>
@@ -767,6 +772,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
     bool at_fence = false;
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
+    int32_t next_fence = do_stats ? (int32_t)((a.k0 / a.stats.stride + 1) * a.stats.stride) : INT32_MAX;   // see run_filter
 
     cta_vote_init(vbuf);
     for (uint32_t iter = 0;; ++iter) {
@@ -813,6 +819,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
                 ++n_sexec;
             }
             at_fence = false;
+            next_fence += a.stats.stride;
         }
         bool serve = true;
         if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
@@ -901,7 +908,7 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
         }
         if (active && !(want && !serve)) {
             ++k;
-            if (do_stats && (k % a.stats.stride) == 0) at_fence = true;
+            if (k == next_fence) at_fence = true;
         }
     }
     if (!live) return;
@@ -965,11 +972,19 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     const bool live = slot < a.st.n;
     const int64_t i = slot;      // (a reordered launch has its arrays in slot order: DeviceState::gid_perm)
     PShared<T, N, BLOCK> P{ sm + threadIdx.x };
+#ifdef QEKF_EXP8
+    int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * ((sizeof(T) == 8 && N == 15) ? 105 : N * (N + 1) / 2));
+#else
     int *vbuf = reinterpret_cast<int *>(sm + (size_t)BLOCK * (N * (N + 1) / 2));
+#endif
     // behind the vote words: the sequencer's integers, then a copy of the launch-wide constants for the out-of-line calls
     int32_t *scr = vbuf + VOTE_WORDS;
     Consts<T> *csm = reinterpret_cast<Consts<T> *>(scr + (size_t)BLOCK * (MR ? MR_SCRATCH_INTS : SR_SCRATCH_INTS));
+#ifndef QEKF_EXP8
     copy_consts(csm, a.c);             // (published by the barrier of cta_vote_init)
+#else
+    csm = nullptr;
+#endif
     // padding lanes still take part in the votes
     if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
     else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);

@@ -12,7 +12,11 @@ namespace qekf {
 // warps, but the register file decides: 12 warps at 168 registers beat 14 at 128 by 17 % (and 8 at 255, which
 // does not spill at all, is as fast as 12); one lockstep CTA rather than two independent 224-thread ones, which
 // drift apart and thrash the instruction cache (no_instruction 1.0 per issue in profiles/r1_13_fp32.md).
+#ifdef QEKF_EXP8   // timing experiment only (results are wrong): 8 warps, the last 15 packed covariance elements aliased
+template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 384 : 256; };
+#else
 template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 384 : 224; };
+#endif
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
 cudaError_t launch_run(const RunArgs<T> &a, unsigned grid, size_t smem, cudaStream_t stream);

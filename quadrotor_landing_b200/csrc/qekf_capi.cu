@@ -126,9 +126,15 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
 int block_of(const qekf_handle *h) { return h->precision == QEKF_FP64 ? BlockOf<double>::value : BlockOf<float>::value; }
 size_t smem_bytes(const qekf_handle *h)
 {
+#ifdef QEKF_EXP8
+    size_t b = (size_t)block_of(h) * ((h->precision == QEKF_FP64 && h->np == 120) ? 105 : h->np) * h->tsize + VOTE_WORDS * sizeof(int);
+#else
     size_t b = (size_t)block_of(h) * h->np * h->tsize + VOTE_WORDS * sizeof(int);
+#endif
     b += (size_t)block_of(h) * (h->p.multirate_ekf ? MR_SCRATCH_INTS : SR_SCRATCH_INTS) * sizeof(int32_t);
+#ifndef QEKF_EXP8
     b += consts_smem_bytes(h->precision == QEKF_FP64 ? sizeof(Consts<double>) : sizeof(Consts<float>));
+#endif
     return b;
 }
 unsigned grid_of(const qekf_handle *h) { return (unsigned)((h->n + block_of(h) - 1) / block_of(h)); }
