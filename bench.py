@@ -73,21 +73,53 @@ def bench_noise(q, first_global_id=0):
     return n
 
 
-def apply_sweep(q, b, p, N, seed):
-    """BASELINE config 5: every filter gets its own process / measurement noise and camera extrinsic."""
+def sweep_values(q, p, N, seed):
+    """BASELINE config 5: every filter gets its own process / measurement noise and camera extrinsic ({field: [dim][N]})."""
     rng = np.random.default_rng(seed)
     base_q = np.array(list(p.Q_a) + list(p.Q_w) + list(p.Q_ab) + list(p.Q_wb))
     base_r = np.array(list(p.R_r) + list(p.R_ang))
-    b.set_filter_params(q.PF_Q, base_q[:, None] * 10 ** rng.uniform(-1, 1, size=(12, N)))
-    b.set_filter_params(q.PF_R, base_r[:, None] * 10 ** rng.uniform(-1, 1, size=(6, N)))
-    b.set_filter_params(q.PF_R_V_CV, np.array(list(p.r_v_cv))[:, None] + rng.uniform(-0.02, 0.02, size=(3, N)))
+    out = {q.PF_Q: base_q[:, None] * 10 ** rng.uniform(-1, 1, size=(12, N)),
+           q.PF_R: base_r[:, None] * 10 ** rng.uniform(-1, 1, size=(6, N)),
+           q.PF_R_V_CV: np.array(list(p.r_v_cv))[:, None] + rng.uniform(-0.02, 0.02, size=(3, N))}
     ang = rng.normal(scale=np.deg2rad(1.0) / 2, size=(3, N))                 # small rotation about a random axis
     dq = np.concatenate([ang, np.sqrt(1 - (ang ** 2).sum(axis=0))[None]])   # x, y, z, w
     qv = np.array(list(p.q_vc))
     x1, y1, z1, w1 = qv[:, None] * np.ones((4, N))
     x2, y2, z2, w2 = dq
-    b.set_filter_params(q.PF_Q_VC, np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
-                                             w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]))
+    out[q.PF_Q_VC] = np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                               w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+    return out
+
+
+def apply_sweep(q, b, p, N, seed):
+    vals = sweep_values(q, p, N, seed)
+    for field, v in vals.items():
+        b.set_filter_params(field, v)
+    return vals
+
+
+def facade_latency(seconds=20):
+    """N = 1 drop-in: host latency of RelativePoseEKF::filter_update through include/relative_pose_ekf_gpu.hpp (one launch
+    + one synchronisation per tick), measured by the C++ replay driver (tools/replay_driver.cpp) on the rotors preset,
+    delayed fusion and single rate.  Outside every timed region; None when the driver binary is not built."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "quadrotor_landing_b200", "bin", "qekf_replay")
+    preset = os.path.join(ROOT, "quadrotor_landing_b200", "presets", "rotors_sim.yaml")
+    if not (os.path.exists(exe) and os.path.exists(preset)):
+        return None
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, extra in (("delayed_fusion", []), ("single_rate", ["--single-rate"])):
+            try:
+                res = subprocess.run([exe, "--preset", preset, "--seconds", str(seconds), "--out", os.path.join(tmp, "t.csv")] + extra,
+                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+                ln = [l for l in res.stdout.splitlines() if "tick_latency_us" in l][-1]
+                out[name] = json.loads(ln.split("qekf_replay: ", 1)[1])["tick_latency_us"]
+            except Exception as e:  # noqa: BLE001 -- a diagnostic leg must not take the bench line down
+                out[name] = {"error": str(e)[:120]}
+    out["what"] = "per-tick host latency (us) of the C++ facade's filter_update, update_freq from the preset"
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -520,6 +552,10 @@ def run_ours(args):
                                           % (sample, T, dt, CPU_NOTE),
                                 "single_thread": {"value": 32 * T / dt1, "unit": "filter-steps/s", "cores": 1,
                                                   "sample": "32 filters x %d ticks, %.1f s" % (T, dt1)}}
+    if world == 1 and default_main:
+        lat = facade_latency()
+        if lat:
+            line["facade_latency"] = lat
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -322,6 +322,9 @@ template <typename T, class PAR> struct RotPar {
     QEKF_FN T g(int a) const { return sm_ld(gs9 + (RC_G + a)); }
     QEKF_FN T ab_static(int a) const { return sm_ld(gs9 + (RC_ABS + a)); }
     QEKF_FN T wb_static(int a) const { return sm_ld(gs9 + (RC_WBS + a)); }
+    QEKF_FN T dT() const { return c.dT; }
+    QEKF_FN T small_ang_tol() const { return c.small_ang_tol; }
+    QEKF_FN T cov_init(int i) const { return c.cov_init[i]; }
 };
 // the launch-wide parameters entirely from this role's relabelled copy
 template <typename T> struct ParS {
@@ -340,6 +343,9 @@ template <typename T> struct ParS {
     QEKF_FN T g(int a) const { return sm_ld(rc + (RC_G + a)); }
     QEKF_FN T ab_static(int a) const { return sm_ld(rc + (RC_ABS + a)); }
     QEKF_FN T wb_static(int a) const { return sm_ld(rc + (RC_WBS + a)); }
+    QEKF_FN T dT() const { return c.dT; }
+    QEKF_FN T small_ang_tol() const { return c.small_ang_tol; }
+    QEKF_FN T cov_init(int i) const { return c.cov_init[i]; }
 };
 // fill one role's copy rc[RC_N] (plain memory) from the launch-wide constants
 template <typename T> QEKF_FN void fill_role_consts(const Consts<T> &c, int role, T *rc)

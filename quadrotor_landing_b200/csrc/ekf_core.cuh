@@ -118,6 +118,13 @@ template <typename T> struct ParU {
     QEKF_FN T q_vc(int i) const { return c.q_vc[i]; }
     QEKF_FN double meas_delay() const { return c.meas_delay; }
     QEKF_FN double dyn_offset() const { return c.dyn_offset; }
+    // launch-wide scalars the step functions need
+    QEKF_FN T dT() const { return c.dT; }
+    QEKF_FN T g(int i) const { return c.g[i]; }
+    QEKF_FN T ab_static(int i) const { return c.ab_static[i]; }
+    QEKF_FN T wb_static(int i) const { return c.wb_static[i]; }
+    QEKF_FN T small_ang_tol() const { return c.small_ang_tol; }
+    QEKF_FN T cov_init(int i) const { return c.cov_init[i]; }
 };
 template <typename T> struct ParF {
     const Consts<T> &c;
@@ -134,7 +141,78 @@ template <typename T> struct ParF {
     QEKF_FN T q_vc(int i) const { return t[(PF_QVC + i) * ld]; }
     QEKF_FN double meas_delay() const { return dl[0]; }
     QEKF_FN double dyn_offset() const { return dl[ld]; }
+    QEKF_FN T dT() const { return c.dT; }
+    QEKF_FN T g(int i) const { return c.g[i]; }
+    QEKF_FN T ab_static(int i) const { return c.ab_static[i]; }
+    QEKF_FN T wb_static(int i) const { return c.wb_static[i]; }
+    QEKF_FN T small_ang_tol() const { return c.small_ang_tol; }
+    QEKF_FN T cov_init(int i) const { return c.cov_init[i]; }
 };
+
+#ifdef __CUDACC__
+// The same two views over a copy of the constant block in SHARED memory, for code behind a real call (advance_call,
+// correction_call): a reference to the kernel parameters that crosses a call turns into generic loads from their
+// global-memory image (L2 latency), a generic pointer to a shared copy into generic loads the compiler must treat as
+// long-latency; an explicit ld.shared is a 29-cycle access it can schedule.  The asm statements are deliberately not
+// volatile: the block never changes during a launch, so they may be hoisted, merged and dropped like any pure load.
+template <typename T> __device__ __forceinline__ T lds_at(uint32_t addr);
+template <> __device__ __forceinline__ double lds_at<double>(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ float lds_at<float>(uint32_t addr)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+#define QEKF_CS_OFF(member) ((uint32_t)__builtin_offsetof(Consts<T>, member))
+template <typename T> struct ParUS {
+    uint32_t base;       // shared-state-space address of the Consts<T> copy
+    __device__ __forceinline__ T at(uint32_t off, int i) const { return lds_at<T>(base + off + (uint32_t)i * (uint32_t)sizeof(T)); }
+    __device__ __forceinline__ T Q(int i) const { return at(QEKF_CS_OFF(Q), i); }
+    __device__ __forceinline__ T Ra(int i) const { return at(QEKF_CS_OFF(Ra), i); }
+    __device__ __forceinline__ T RC(int i) const { return at(QEKF_CS_OFF(RC), i); }
+    __device__ __forceinline__ T RA(int i) const { return at(QEKF_CS_OFF(RA), i); }
+    __device__ __forceinline__ T D(int i) const { return at(QEKF_CS_OFF(D), i); }
+    __device__ __forceinline__ T C_vc(int i) const { return at(QEKF_CS_OFF(C_vc), i); }
+    __device__ __forceinline__ T r_v_cv(int i) const { return at(QEKF_CS_OFF(r_v_cv), i); }
+    __device__ __forceinline__ T q_vc(int i) const { return at(QEKF_CS_OFF(q_vc), i); }
+    __device__ __forceinline__ double meas_delay() const { return lds_at<double>(base + QEKF_CS_OFF(meas_delay)); }
+    __device__ __forceinline__ double dyn_offset() const { return lds_at<double>(base + QEKF_CS_OFF(dyn_offset)); }
+    __device__ __forceinline__ T dT() const { return at(QEKF_CS_OFF(dT), 0); }
+    __device__ __forceinline__ T g(int i) const { return at(QEKF_CS_OFF(g), i); }
+    __device__ __forceinline__ T ab_static(int i) const { return at(QEKF_CS_OFF(ab_static), i); }
+    __device__ __forceinline__ T wb_static(int i) const { return at(QEKF_CS_OFF(wb_static), i); }
+    __device__ __forceinline__ T small_ang_tol() const { return at(QEKF_CS_OFF(small_ang_tol), 0); }
+    __device__ __forceinline__ T cov_init(int i) const { return at(QEKF_CS_OFF(cov_init), i); }
+};
+template <typename T> struct ParFS {
+    uint32_t base;
+    const T *t;
+    const double *dl;
+    int64_t ld;
+    __device__ __forceinline__ T at(uint32_t off, int i) const { return lds_at<T>(base + off + (uint32_t)i * (uint32_t)sizeof(T)); }
+    __device__ __forceinline__ T Q(int i) const { return t[(PF_Q + i) * ld]; }
+    __device__ __forceinline__ T Ra(int i) const { return t[(PF_RA + i) * ld]; }
+    __device__ __forceinline__ T RC(int i) const { return t[(PF_RC + i) * ld]; }
+    __device__ __forceinline__ T RA(int i) const { return t[(PF_RAS + i) * ld]; }
+    __device__ __forceinline__ T D(int i) const { return t[(PF_D + i) * ld]; }
+    __device__ __forceinline__ T C_vc(int i) const { return t[(PF_CVC + i) * ld]; }
+    __device__ __forceinline__ T r_v_cv(int i) const { return t[(PF_RVCV + i) * ld]; }
+    __device__ __forceinline__ T q_vc(int i) const { return t[(PF_QVC + i) * ld]; }
+    __device__ __forceinline__ double meas_delay() const { return dl[0]; }
+    __device__ __forceinline__ double dyn_offset() const { return dl[ld]; }
+    __device__ __forceinline__ T dT() const { return at(QEKF_CS_OFF(dT), 0); }
+    __device__ __forceinline__ T g(int i) const { return at(QEKF_CS_OFF(g), i); }
+    __device__ __forceinline__ T ab_static(int i) const { return at(QEKF_CS_OFF(ab_static), i); }
+    __device__ __forceinline__ T wb_static(int i) const { return at(QEKF_CS_OFF(wb_static), i); }
+    __device__ __forceinline__ T small_ang_tol() const { return at(QEKF_CS_OFF(small_ang_tol), 0); }
+    __device__ __forceinline__ T cov_init(int i) const { return at(QEKF_CS_OFF(cov_init), i); }
+};
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // packed symmetric covariance storage.  Element (i,j), i<=j, lives at index i*N - i(i-1)/2 + (j-i).
@@ -412,7 +490,6 @@ template <typename T> QEKF_FN void phi_matrix(const PhiCoef<T> &pc, const T dth[
 template <typename T, bool BIAS, class PS, class PAR>
 QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const PAR &par, bool reinit_bias)
 {
-    const Consts<T> &c = par.c;
     T qq[4], Cvc[9];
     {
         T qvc[4] = { par.q_vc(0), par.q_vc(1), par.q_vc(2), par.q_vc(3) };
@@ -438,7 +515,7 @@ QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const PAR &p
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = i; j < N; ++j) P.st(i, j, (i == j) ? c.cov_init[i / 3] : T(0));
+        for (int j = i; j < N; ++j) P.st(i, j, (i == j) ? par.cov_init(i / 3) : T(0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,22 +532,21 @@ template <typename T> struct PredJac { T A[9], B[9], Phi[9], QV[6]; };
 template <typename T, class PAR>
 QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3], PredJac<T> &J)
 {
-    const Consts<T> &c = par.c;
-    const T d = c.dT;
+    const T d = par.dT();
     T *A = J.A, *B = J.B, *Phi = J.Phi, *QV = J.QV;
     {
         T a[3], w[3], C[9];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            a[i] = u[i] - s.ab[i] - c.ab_static[i];
-            w[i] = u[3 + i] - s.wb[i] - c.wb_static[i];
+            a[i] = u[i] - s.ab[i] - par.ab_static(i);
+            w[i] = u[3 + i] - s.wb[i] - par.wb_static(i);
         }
         quat_to_rot(s.q, C);
         T acc[3];
         mv(C, a, acc);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            acc[i] += c.g[i];
+            acc[i] += par.g(i);
             accel[i] = acc[i];
             s.r[i] = M<T>::fma_(d, s.v[i], s.r[i]);   // uses the old v (explicit Euler)
         }
@@ -500,7 +576,7 @@ QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3
         // attitude: q <- normclip(q (x) exp(dT w)); Phi = I - skew(dT w) or Rodrigues(-|dT w|)
         T dth[3] = { d * w[0], d * w[1], d * w[2] };
         PhiCoef<T> pc;
-        attitude_step(s.q, dth, c.small_ang_tol, pc);
+        attitude_step(s.q, dth, par.small_ang_tol(), pc);
         phi_matrix(pc, dth, Phi);
     }
 }
@@ -509,7 +585,7 @@ QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3
 template <typename T, bool BIAS, class PS, class PAR>
 QEKF_FN void pred_cov(PS &P, const PredJac<T> &J, const PAR &par)
 {
-    const T d = par.c.dT;
+    const T d = par.dT();
     const T *A = J.A, *B = J.B, *Phi = J.Phi, *QV = J.QV;
     // ---- E1: dr += dT dv -------------------------------------------------------------------
     {

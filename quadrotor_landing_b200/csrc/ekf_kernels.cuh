@@ -7,6 +7,8 @@
 // the IMU sample of tick k is latched, then the tick runs.
 #pragma once
 
+#include <type_traits>
+
 #include "ekf_core.cuh"
 #include "ekf_synth.cuh"
 
@@ -63,11 +65,20 @@ template <typename T> struct DeviceState {
     const int32_t *gid_perm;
 };
 
-// the parameter view of filter i: launch-wide constants, or this filter's column of the override table
+// the parameter view of filter i: launch-wide constants, or this filter's column of the override table.
+// cold<CSM>: what the out-of-line calls read the constants through -- the same view (CSM = false: host instantiation,
+// per-tick kernel) or the view over the CTA's shared-memory copy of the constant block (CSM = true: the fused replay).
 template <typename T, bool PF> struct ParSel;
 template <typename T> struct ParSel<T, false> {
     using type = ParU<T>;
     static QEKF_FN type make(const Consts<T> &c, const DeviceState<T> &, int64_t) { return type{ c }; }
+    static QEKF_FN type make_cold(const type &par, const Consts<T> *, const DeviceState<T> &, int64_t, std::false_type) { return par; }
+#ifdef __CUDACC__
+    static __device__ __forceinline__ ParUS<T> make_cold(const type &, const Consts<T> *csm, const DeviceState<T> &, int64_t, std::true_type)
+    {
+        return ParUS<T>{ (uint32_t)__cvta_generic_to_shared(csm) };
+    }
+#endif
 };
 template <typename T> struct ParSel<T, true> {
     using type = ParF<T>;
@@ -75,6 +86,13 @@ template <typename T> struct ParSel<T, true> {
     {
         return type{ c, st.pf + i, st.pf_delay + i, st.ld };
     }
+    static QEKF_FN type make_cold(const type &par, const Consts<T> *, const DeviceState<T> &, int64_t, std::false_type) { return par; }
+#ifdef __CUDACC__
+    static __device__ __forceinline__ ParFS<T> make_cold(const type &, const Consts<T> *csm, const DeviceState<T> &st, int64_t i, std::true_type)
+    {
+        return ParFS<T>{ (uint32_t)__cvta_generic_to_shared(csm), st.pf + i, st.pf_delay + i, st.ld };
+    }
+#endif
 };
 
 // Input streams as seen by the kernel.  Element (k, c) of filter i lives at base[(k*6+c)*cs + i*is]:
@@ -468,17 +486,15 @@ constexpr int SR_SCRATCH_INTS = 16;
 // Statistics fence: a lane that has finished a sampling tick waits until every lane of the CTA has, then all
 // sample together (one execution of the sampling code per stride; the time skew is back to zero).
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
-template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS, bool CSM = false>
 QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
                         const bool live = true, int *vbuf = nullptr, const Consts<T> *c_cold = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
     const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
-    // what the out-of-line calls read the launch-wide constants through: a reference to kernel parameters turns into
-    // generic loads from their global-memory image once it crosses a call (L2 latency with this kernel's squeezed L1);
-    // the kernels therefore hand over a shared-memory copy
-    const typename ParSel<T, PF>::type par_cold = ParSel<T, PF>::make(c_cold ? *c_cold : a.c, a.st, i);
+    // what the out-of-line calls read the launch-wide constants through (ParSel::make_cold)
+    const auto par_cold = ParSel<T, PF>::make_cold(par, c_cold, a.st, i, std::integral_constant<bool, CSM>());
     const int32_t k_end = (int32_t)(a.k0 + a.n_steps);       // (qekf_run bounds tick indices to 31 bits)
     Nominal<T> s;
     SmemInt flags{ scr + 0 * scr_stride }, upds{ scr + 1 * scr_stride }, n_pred{ scr + 2 * scr_stride };
@@ -677,6 +693,15 @@ QEKF_FN void store_checkpoint(const DeviceState<T> &st, int64_t i, const Nominal
     store_filter<T>(v, i, s, P);
 }
 
+template <typename T> QEKF_FN void prefetch_l2(const T *p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // n consecutive prediction_steps through the stored IMU inputs of ring slots first, first+1, ... (mod L).
 // (Streaming loads / stores, __ldcs / __stcs, for the ring were measured and cost 8 %: 4.17e9 -> 3.86e9 filter-steps/s.)
 // One out-of-line copy of the prediction code serves the replay before a delayed correction, the checkpoint
@@ -694,14 +719,17 @@ QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_
     for (int cc = 0; cc < 6; ++cc) u[cc] = ring_i[((int64_t)slot * 6 + cc) * ld];
     for (int32_t j = 0; j < n; ++j) {
         slot = (slot + 1 == L) ? 0 : slot + 1;
-        T un[6];
-        if (j + 1 < n) {                 // software prefetch of the next entry's input
+        // the next entry's input: asked for now (an L2 prefetch holds no registers through the prediction, where a
+        // register prefetch cost 12 and pushed as many values of the covariance code into local memory), loaded after
+        if (j + 1 < n) {
 #pragma unroll
-            for (int cc = 0; cc < 6; ++cc) un[cc] = ring_i[((int64_t)slot * 6 + cc) * ld];
+            for (int cc = 0; cc < 6; ++cc) prefetch_l2(ring_i + ((int64_t)slot * 6 + cc) * ld);
         }
         prediction_step<T, BIAS>(s, P, u, par, acc);
+        if (j + 1 < n) {
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) u[cc] = un[cc];
+            for (int cc = 0; cc < 6; ++cc) u[cc] = ring_i[((int64_t)slot * 6 + cc) * ld];
+        }
     }
     *sp = s;
     accel_out[0] = acc[0]; accel_out[1] = acc[1]; accel_out[2] = acc[2];
@@ -720,14 +748,14 @@ QEKF_COLD void advance_call(Nominal<T> *sp, PS &P, const PAR par, const T *ring_
 // step delay), so every index a future correction can address is still reachable.  Lanes that do not correct
 // (tag dropout, rejected detection) catch their checkpoint up to size-D inside their CTA-mates' correction
 // events, where the warp executes prediction code anyway.
-template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS>
+template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool PF, class PS, bool CSM = false>
 QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
                            const bool live = true, int *vbuf = nullptr, const Consts<T> *c_cold = nullptr)
 {
     const Consts<T> &c = a.c;
     const int64_t i = live ? i_in : 0;
     const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
-    const typename ParSel<T, PF>::type par_cold = ParSel<T, PF>::make(c_cold ? *c_cold : a.c, a.st, i);   // see run_filter
+    const auto par_cold = ParSel<T, PF>::make_cold(par, c_cold, a.st, i, std::integral_constant<bool, CSM>());   // see run_filter
     const int64_t k_end = a.k0 + a.n_steps;
     const int32_t L = a.st.ring_len, Dm1 = a.st.dmax_m1;
     T *ring_i = a.st.ring + i;
@@ -986,8 +1014,13 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
     csm = nullptr;
 #endif
     // padding lanes still take part in the votes
+#ifndef QEKF_EXP8
+    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    else run_filter<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+#else
     if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
     else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -104,3 +104,36 @@ def test_full_size_delayed_fusion():
     npred, ncorr = b.step_counts()
     assert npred < 1.15 * N * scn.T                                      # lazily evaluated history: ~1.08 predictions per tick
     b.close()
+
+
+def test_full_size_config5_sweep_delayed_dynamic():
+    """BASELINE config 5 at full size: 1,048,576 filters x 12,000 ticks, every filter with its own Q, R and camera
+    extrinsic (qekf_set_filter_params), delayed-measurement fusion with the stamp-derived (dynamic) delay -- the
+    workload of bench.py --sweep --multirate --dynamic-delay.  Windows of the id range against the oracle carrying
+    the same per-filter parameter sets and the reference's full history vectors (relative_pose_EKF.cpp:196-264); the
+    whole batch through the statistics."""
+    p = bench.bench_params(q, multirate=True, dynamic=True)
+    scn = bench.bench_scenario(q, p)
+    noise = bench.bench_noise(q)
+    N, stride = 1 << 20, 200
+    nb = scn.T // stride
+    b = q.BatchEKF(p, N)
+    vals = bench.apply_sweep(q, b, p, N, seed=1234)
+    b.stats_configure(nb, stride)
+    b.run_monte_carlo(scn, noise, 0, 6007)
+    b.run_monte_carlo(scn, noise, 6007, scn.T - 6007)
+    stats = b.stats()
+    assert np.array_equal(stats[:, 16], np.full(nb, float(N)))          # every filter sampled once per second
+    # (a sweep over two decades of Q and R is allowed a few inconsistent filters, but no non-finite state)
+    assert stats[:, 18].sum() <= 1e-5 * stats[:, 16].sum()
+    for first, count in [(0, 40), (N // 2 - 13, 32), (N - 40, 40)]:
+        st = b.synthesize_streams(scn, noise, first, count)
+        ob = orc.Batch(orc.params_from(p), count)
+        for field, v in vals.items():
+            ob.set_filter_params(field, np.ascontiguousarray(v[:, first:first + count]))
+        ob.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+        assert norm_rel(b.state(first, count), ob.state()) < TOL and norm_rel(b.cov(first, count), ob.cov()) < TOL
+        assert np.array_equal(b.flags(first, count), ob.flags())          # incl. x_hist.size()
+        assert norm_rel(b.aux(first, count), ob.aux()) < TOL              # incl. measurement_delay_curr
+    assert np.isfinite(b.state()).all()
+    b.close()
