@@ -208,7 +208,7 @@ def run_reference(args):
                          "sample": "%d filters x %d ticks per step; %s" % (sample, scn.T, CPU_NOTE)},
         "e2e": {"value": rate, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, scn, cpu_sample=None):
@@ -418,12 +418,11 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line.  NCCL's own log (communicator init: "... nranks N ...") is evidence the
-        # driver wants, so it is not silenced: it goes to stderr, at INFO for the INIT subsystem unless the
-        # environment already says otherwise.
+        # NCCL's own log (communicator init: "... nranks N ...") is evidence the driver wants, so it is not silenced: it
+        # is on at INFO for the INIT subsystem unless the environment already says otherwise, and reaches stderr with
+        # everything else that is written to fd 1 (claim_stdout).
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     N = args.filters
@@ -556,12 +555,37 @@ def run_ours(args):
         lat = facade_latency()
         if lat:
             line["facade_latency"] = lat
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Everything else any library writes to file descriptor 1 (NCCL's version
+    banner and its INFO log, which is evidence the driver wants and is therefore left on) is sent to stderr: fd 1 is
+    pointed at fd 2 for the rest of the process and the JSON line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

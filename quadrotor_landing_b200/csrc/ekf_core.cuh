@@ -529,6 +529,7 @@ QEKF_FN void initialize_state(Nominal<T> &s, PS &P, const T tag[7], const PAR &p
 template <typename T> struct PredJac { T A[9], B[9], Phi[9], QV[6]; };
 
 // the nominal half of prediction_step (cpp:346-401): kinematics, and the Jacobian pieces from the pre-update state
+// (Measured: running the attitude step first, so that the rest of the tick is one basic block, costs 2 %.)
 template <typename T, class PAR>
 QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3], PredJac<T> &J)
 {
@@ -581,44 +582,94 @@ QEKF_FN void pred_nominal(Nominal<T> &s, const T u[6], const PAR &par, T accel[3
     }
 }
 
-// the covariance half (cpp:402-414): P <- F P F^T + W Q W^T through the three in-place congruences
+// the covariance half (cpp:402-414): P <- F P F^T + W Q W^T through the three congruences E1, E2, E3.
+// Evaluated block ROW by block row rather than congruence by congruence: the dr row first (its E1 step needs the dv
+// row as it was, and its E2 / E3 steps only the Jacobian pieces), then the dv row (E2, and E3 on its dtheta block),
+// then the dtheta row (E3).  Every element sees the same operations in the same order as the congruence-by-congruence
+// evaluation, so the results are identical to the last bit; what changes is that a block which two or three
+// congruences touch stays in registers in between instead of going through shared memory each time
+// (414 -> 324 block-element accesses per prediction in the source; the shared-memory pipe is the second-busiest unit of
+// the kernel).
 template <typename T, bool BIAS, class PS, class PAR>
 QEKF_FN void pred_cov(PS &P, const PredJac<T> &J, const PAR &par)
 {
     const T d = par.dT();
     const T *A = J.A, *B = J.B, *Phi = J.Phi, *QV = J.QV;
-    // ---- E1: dr += dT dv -------------------------------------------------------------------
+    // ---- dr row: E1 (dr += dT dv) on every block, E2 on (r,v), E3 on (r,th) ---------------------------------------
     {
-        T vv[9], rv[9], rvn[9];
-        ldb(P, BV, BV, vv);
-        ldb(P, BR, BV, rv);
+        T rvn[9], rth[9];
+        {
+            T vv[9], rv[9];
+            ldb(P, BV, BV, vv);
+            ldb(P, BR, BV, rv);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) rvn[i] = M<T>::fma_(d, vv[i], rv[i]);
+            for (int i = 0; i < 9; ++i) rvn[i] = M<T>::fma_(d, vv[i], rv[i]);
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b = a; b < 3; ++b) {
-                T x = P.ld(a, b);
-                x = M<T>::fma_(d, rv[b * 3 + a] + rvn[a * 3 + b], x);
-                P.st(a, b, x);
-            }
-        stb(P, BR, BV, rvn);
-        constexpr int NY = BIAS ? 3 : 1;
-#pragma unroll
-        for (int y = 0; y < NY; ++y) {
-            const int Y = BTH + y;
-            T t[9], sblk[9];
-            ldb(P, BR, Y, t);
-            ldb(P, BV, Y, sblk);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) t[i] = M<T>::fma_(d, sblk[i], t[i]);
-            stb(P, BR, Y, t);
+                for (int b = a; b < 3; ++b) {
+                    T x = P.ld(a, b);
+                    x = M<T>::fma_(d, rv[b * 3 + a] + rvn[a * 3 + b], x);
+                    P.st(a, b, x);
+                }
         }
+        {
+            T sblk[9];
+            ldb(P, BR, BTH, rth);
+            ldb(P, BV, BTH, sblk);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) rth[i] = M<T>::fma_(d, sblk[i], rth[i]);          // (r,th) after E1
+        }
+        T n[9];
+        if (BIAS) {
+            {
+                T rw[9], sblk[9];
+                ldb(P, BR, BWB, rw);
+                ldb(P, BV, BWB, sblk);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) rw[i] = M<T>::fma_(d, sblk[i], rw[i]);
+                stb(P, BR, BWB, rw);                                                       // final: E2, E3 leave (r,wb) alone
+#pragma unroll
+                for (int i = 0; i < 9; ++i) n[i] = -d * rw[i];
+            }
+            {
+                T ra[9], sblk[9];
+                ldb(P, BR, BAB, ra);
+                ldb(P, BV, BAB, sblk);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) ra[i] = M<T>::fma_(d, sblk[i], ra[i]);
+                stb(P, BR, BAB, ra);                                                       // final
+                mmt_acc(rvn, rth, A);                                                      // E2: (r,v) += (r,th) A^T + (r,ab) B^T
+                mmt_acc(rvn, ra, B);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) n[i] = T(0);
+            mmt_acc(rvn, rth, A);
+        }
+        stb(P, BR, BV, rvn);
+        mmt_acc(n, rth, Phi);                                                              // E3: (r,th) Phi^T - dT (r,wb)
+        stb(P, BR, BTH, n);
     }
-    // ---- E2: dv += A dtheta + B dab ----------------------------------------------------------
+    // ---- dv row: E2 (dv += A dtheta + B dab), E3 on (v,th) ---------------------------------------------------------
     {
         T vv[9];
         ldb(P, BV, BV, vv);   // full symmetric copy; only the upper triangle is finally stored
+        T vthn[9];            // (v,th) after E3
+        if (BIAS) {
+            T nw[9], blk[9];
+            ldb(P, BV, BWB, nw);
+            ldb(P, BTH, BWB, blk);
+            mm_acc(nw, A, blk);
+            ldb(P, BAB, BWB, blk);
+            mm_acc(nw, B, blk);
+            stb(P, BV, BWB, nw);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) vthn[i] = -d * nw[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) vthn[i] = T(0);
+        }
         {
             T o[9], n[9], thth[9];
             ldb(P, BV, BTH, o);
@@ -633,48 +684,27 @@ QEKF_FN void pred_cov(PS &P, const PredJac<T> &J, const PAR &par)
             }
             mmt_acc(vv, A, o);     // + A (v,th)_old^T
             mmt_acc(vv, n, A);     // + (v,th)_new A^T
-            stb(P, BV, BTH, n);
+            mmt_acc(vthn, n, Phi); // E3: (v,th) Phi^T - dT (v,wb)
+            stb(P, BV, BTH, vthn);
         }
         if (BIAS) {
-            {
-                T o[9], n[9], blk[9];
-                ldb(P, BV, BAB, o);
+            T o[9], n[9], blk[9];
+            ldb(P, BV, BAB, o);
 #pragma unroll
-                for (int i = 0; i < 9; ++i) n[i] = o[i];
-                ldb(P, BTH, BAB, blk);
-                mm_acc(n, A, blk);
-                ldb(P, BAB, BAB, blk);
-                mm_acc(n, B, blk);
-                mmt_acc(vv, B, o);
-                mmt_acc(vv, n, B);
-                stb(P, BV, BAB, n);
-            }
-            {
-                T n[9], blk[9];
-                ldb(P, BV, BWB, n);
-                ldb(P, BTH, BWB, blk);
-                mm_acc(n, A, blk);
-                ldb(P, BAB, BWB, blk);
-                mm_acc(n, B, blk);
-                stb(P, BV, BWB, n);
-            }
+            for (int i = 0; i < 9; ++i) n[i] = o[i];
+            ldb(P, BTH, BAB, blk);
+            mm_acc(n, A, blk);
+            ldb(P, BAB, BAB, blk);
+            mm_acc(n, B, blk);
+            mmt_acc(vv, B, o);
+            mmt_acc(vv, n, B);
+            stb(P, BV, BAB, n);
         }
         // + W Q W^T on the (v,v) block, then store its upper triangle
         vv[0] += QV[0]; vv[1] += QV[1]; vv[2] += QV[2]; vv[4] += QV[3]; vv[5] += QV[4]; vv[8] += QV[5];
         stb(P, BV, BV, vv);
-        {
-            T rv[9], blk[9];
-            ldb(P, BR, BV, rv);
-            ldb(P, BR, BTH, blk);
-            mmt_acc(rv, blk, A);
-            if (BIAS) {
-                ldb(P, BR, BAB, blk);
-                mmt_acc(rv, blk, B);
-            }
-            stb(P, BR, BV, rv);
-        }
     }
-    // ---- E3: dtheta <- Phi dtheta - dT dwb ---------------------------------------------------
+    // ---- dtheta row: E3 (dtheta <- Phi dtheta - dT dwb) --------------------------------------------------------------
     {
         T thw_o[9], thw_n[9];
         if (BIAS) {
@@ -693,23 +723,6 @@ QEKF_FN void pred_cov(PS &P, const PredJac<T> &J, const PAR &par)
 #pragma unroll
             for (int i = 0; i < 9; ++i) thw_n[i] = -d * ww[i];
             mm_acc(thw_n, Phi, thw_o);
-        }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {   // X = r, v :  (X,th) <- (X,th) Phi^T - dT (X,wb)
-            const int X = BR + x;
-            T xt[9], n[9];
-            ldb(P, X, BTH, xt);
-            if (BIAS) {
-                T xw[9];
-                ldb(P, X, BWB, xw);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) n[i] = -d * xw[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) n[i] = T(0);
-            }
-            mmt_acc(n, xt, Phi);
-            stb(P, X, BTH, n);
         }
         {
             T thth[9], m[9], n[9];
