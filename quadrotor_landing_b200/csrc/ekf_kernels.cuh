@@ -63,6 +63,9 @@ template <typename T> struct DeviceState {
     //              only the noise identity is perm[j] (the thread-per-filter kernels, single-rate and delayed fusion)
     const int32_t *perm;
     const int32_t *gid_perm;
+    // delayed fusion, Monte-Carlo launches: 1 = the entries after every checkpoint are the synthetic IMU samples of this
+    // launch's noise model and scenario, so the replay may re-synthesise them instead of reading the ring (run_filter_mrs)
+    int32_t hist_synth;
 };
 
 // the parameter view of filter i: launch-wide constants, or this filter's column of the override table.
@@ -976,6 +979,276 @@ QEKF_FN void run_filter_mr(const RunArgs<T> &a, const int64_t i_in, PS &P, int32
     for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
 }
 
+// ------------------------------------------------------------------------------------------------
+// delayed-measurement fusion of a Monte-Carlo launch: no ring, no light ticks
+// ------------------------------------------------------------------------------------------------
+// In a Monte-Carlo launch u_hist[k] is a pure function of (seed, filter id, k): the entries after the checkpoint need
+// no storage, they are re-synthesised where the replay consumes them.  A tick that fuses nothing then has no work left
+// at all (the head prediction is implied, its input is implied), so the loop below does not iterate over ticks: every
+// lane jumps straight to its next decision point -- the tick whose measurement gate opens, a sampling boundary, the end
+// of the launch -- handling tag arrivals on the way, and the CTA only meets (one vote, one barrier) where lanes fuse
+// measurements or sample statistics.  Lanes whose tick indices differ (private dropouts) reach their correction ticks
+// in the same iteration, so the time skew costs nothing here.  Same arithmetic on the same inputs as run_filter_mr
+// with SYNTH = true: the results are bit-identical (tests/test_gpu_multirate.py, test_gpu_reorder.py).
+
+// n consecutive prediction_steps whose inputs are the synthesised IMU samples of ticks tick0, tick0+1, ...
+// bz: the true bias' six normals (shared-memory scratch, stride bz_stride).  ring_out != nullptr: the samples are also
+// written to ring slots 0, 1, ... of this filter (the launch epilogue leaves a valid ring behind for the entry points
+// that read it: per-tick interface, explicit streams).
+template <typename T, bool BIAS, class PS, class PAR>
+QEKF_COLD void advance_synth_call(Nominal<T> *sp, PS &P, const PAR par, const double *imu_clean, const ImuSynth nz, int64_t gid,
+                                  const float *bz, int bz_stride, int32_t tick0, int32_t n, T *accel_out, T *ring_out, int64_t ld)
+{
+    if (n <= 0) return;
+    Nominal<T> s = *sp;
+    T acc[3] = { accel_out[0], accel_out[1], accel_out[2] };
+    for (int32_t j = 0; j < n; ++j) {
+        const int64_t k = (int64_t)tick0 + j;
+        T u[6];
+        {
+            double raw[6], tb[6], ud[6];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) raw[cc] = imu_clean[k * 6 + cc];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) tb[cc] = (double)(cc < 3 ? nz.sig_ba : nz.sig_bw) * (double)bz[cc * bz_stride];
+            synth_imu(nz, gid, k, raw, tb, ud);
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
+        }
+        if (ring_out) {
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) ring_out[((int64_t)j * 6 + cc) * ld] = u[cc];
+        }
+        prediction_step<T, BIAS>(s, P, u, par, acc);
+    }
+    *sp = s;
+    accel_out[0] = acc[0]; accel_out[1] = acc[1]; accel_out[2] = acc[2];
+}
+
+template <typename T, bool BIAS, bool DIRECT, bool PF, class PS, bool CSM = false>
+QEKF_FN void run_filter_mrs(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t *scr, const int scr_stride,
+                            const bool live = true, int *vbuf = nullptr, const Consts<T> *c_cold = nullptr)
+{
+    const Consts<T> &c = a.c;
+    const int64_t i = live ? i_in : 0;
+    const typename ParSel<T, PF>::type par = ParSel<T, PF>::make(a.c, a.st, i);
+    const auto par_cold = ParSel<T, PF>::make_cold(par, c_cold, a.st, i, std::integral_constant<bool, CSM>());
+    const int32_t k_end = (int32_t)(a.k0 + a.n_steps);
+    const int32_t Dm1 = a.st.dmax_m1;
+    Nominal<T> s;                      // the checkpoint
+    SmemInt flags{ scr + 0 * scr_stride }, upds{ scr + 1 * scr_stride }, nh{ scr + 2 * scr_stride };
+    SmemInt hlen{ scr + 4 * scr_stride }, m{ scr + 5 * scr_stride };
+    SmemInt next_tag_step{ scr + 6 * scr_stride }, pend_m{ scr + 7 * scr_stride }, held{ scr + 8 * scr_stride };
+    SmemInt k{ scr + 9 * scr_stride };
+    SmemInt n_pred{ scr + 16 * scr_stride }, pstart{ scr + 17 * scr_stride };
+    const float *bz = reinterpret_cast<const float *>(scr) + 10 * scr_stride;
+    flags = 0; upds = 0; nh = 0; hlen = 0; n_pred = 0; pstart = INT32_MAX;
+    T accel[3] = { T(0), T(0), T(0) };
+    Inputs<T, true> in;
+    k = k_end;
+    if (live) {
+        load_checkpoint<T>(a.st, i, s, P);
+        flags = a.st.flags[i];
+        upds = a.st.upds[i];
+        nh = a.st.nh[i]; hlen = a.st.hlen[i];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) accel[cc] = a.st.aux[cc * a.st.ld + i];
+        in.init(a, i, a.st.gid_perm ? (int64_t)a.st.gid_perm[i] : i);
+        k = (int32_t)a.k0;
+        pstart = in.priv_start;
+        float z[6];
+        normals6(a.ns, in.gid, STREAM_BIAS, 0u, z);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) reinterpret_cast<float *>(scr)[(10 + cc) * scr_stride] = z[cc];
+    }
+    const ImuSynth nz{ a.ns.seed, a.ns.sig_a, a.ns.sig_w, a.ns.sig_ba, a.ns.sig_bw };
+    // advance *sp by n entries starting with the input of tick t0
+    auto advance = [&](Nominal<T> *sp, int32_t t0, int32_t n, T *acc, T *ring_out) {
+        advance_synth_call<T, BIAS>(sp, P, par_cold, a.in.imu, nz, in.gid, bz, scr_stride, t0, n, acc, ring_out, a.st.ld);
+        if (n > 0) n_pred += n;
+    };
+
+    uint32_t n_corr = 0, n_iter = 0, n_sexec = 0;
+    m = a.m0;
+    next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+    pend_m = -1;
+    held = 0;
+    bool at_fence = false;
+    const bool do_stats = a.stats.acc != nullptr;
+    const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
+    int32_t next_fence = do_stats ? (int32_t)((a.k0 / a.stats.stride + 1) * a.stats.stride) : INT32_MAX;
+
+    cta_vote_init(vbuf);
+    for (uint32_t iter = 0;; ++iter) {
+        // ---- to this lane's next decision point: the tag callbacks on the way (node.cpp:153-176), and every tick that
+        //      fuses nothing as counters only (its entry joins the history: cpp:240-257) ----
+        bool want = false;
+        if (k < k_end && !at_fence) {
+            for (;;) {
+                if (k == next_tag_step) {
+                    if (in.valid(a.in, a.ns, m, (int32_t)k, pstart)) {
+                        pend_m = m;
+                        flags |= FLAG_READY;
+                        if (!(flags & FLAG_INIT)) {
+                            T tag0[7];
+                            in.tag(a.in, a.ns, m, tag0);
+                            initialize_state<T, BIAS>(s, P, tag0, par, false);
+                            flags |= FLAG_INIT;
+                            nh = 0; hlen = 1;                    // history <- single entry (cpp:326-339)
+                        }
+                    }
+                    ++m;
+                    next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+                }
+                const int32_t fl = flags, up = upds, kk = k;
+                const bool init = (fl & FLAG_INIT) != 0, armed = init && (fl & FLAG_READY);
+                // ticks until the gate of cpp:147 opens (0: this tick fuses)
+                const int32_t t_gate = !armed ? INT32_MAX : (c.limit_measurement_freq ? max(0, c.upd_per_meas - 1 - up) : 0);
+                if (t_gate == 0) { want = true; break; }
+                int32_t q = min(min(t_gate, next_tag_step - kk), min(next_fence - kk, k_end - kk));   // >= 1
+                if (init) {
+                    nh += q; hlen += q; upds = up + q;
+                    flags = (fl & ~FLAG_CORRECTED) | FLAG_ACTIVE;
+                }
+                k = kk + q;
+                if (kk + q == next_fence) { at_fence = true; break; }     // tick k-1 was a sampling tick
+                if (kk + q >= k_end) break;
+            }
+        }
+        const bool active = (k < k_end) && !at_fence;
+        const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
+        if (v.active == 0 && v.at_fence == 0) break;
+        ++n_iter;
+        if (do_stats && v.fenced == v.lanes && v.at_fence != 0) {
+            // look at the head: bring the checkpoint as far as any future correction allows, park it, replay the rest on
+            // a copy, sample, come back
+            const bool mine = live && at_fence && (flags & FLAG_INIT);
+            Nominal<T> head = s;
+            if (mine) {
+                const int32_t n_c = (nh > Dm1) ? nh - Dm1 : 0;
+                T scratch[3] = { T(0), T(0), T(0) };
+                advance(&s, k - nh, n_c, scratch, nullptr);
+                nh -= n_c;
+                head = s;
+                store_checkpoint<T>(a.st, i, s, P);
+                advance(&head, k - nh, nh, accel, nullptr);
+            }
+            double tb[6] = { 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) tb[cc] = (double)(cc < 3 ? nz.sig_ba : nz.sig_bw) * (double)bz[cc * scr_stride];
+            stats_sample<T, BIAS>(a, i, (int64_t)k - 1, head, P, tb, mine);
+            if (mine) {
+                load_checkpoint<T>(a.st, i, s, P);
+                ++n_sexec;
+            }
+            at_fence = false;
+            next_fence += a.stats.stride;
+        }
+        bool serve = true;
+        if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
+        const bool event = (v.want != 0) && serve;       // CTA-uniform: corrections are being served now
+        if (want && !serve) ++held;
+        const bool exec = want && serve;                 // (a lane that wants is active and initialised)
+
+        // ---- consume the measurement, corner-margin gate (cpp:150-186) ----
+        bool perform = false;
+        T tag[7];
+        double stamp = 0;
+        if (exec) {
+            if (pend_m >= 0) {
+                in.tag(a.in, a.ns, pend_m, tag);
+                stamp = a.in.tag_stamp[pend_m];
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
+                stamp = a.st.pend[7 * a.st.ld + i];
+            }
+            flags &= ~FLAG_READY;
+            perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
+            held = 0;
+        }
+        // ---- how far this lane moves its checkpoint now ----
+        int32_t n_adv = 0;
+        if (perform) {
+            // cpp:199-201
+            const double t_curr = a.in.t_start + (double)k / a.in.update_freq;
+            const double delay = c.dynamic_meas_delay ? fmin(t_curr - stamp + par.dyn_offset(), c.meas_delay_max)
+                                                      : par.meas_delay();
+            int32_t step = (int32_t)(delay / c.dT_nom + 0.5);
+            if (step < 1) step = 1;
+            int32_t ind = hlen - step;
+            if (ind < 0) ind = 0;
+            n_adv = ind - (hlen - 1 - nh);               // >= 0: the checkpoint never passes entry size-D
+            if (n_adv < 0) n_adv = 0;
+            a.st.aux[10 * a.st.ld + i] = (T)delay;       // measurement_delay_curr
+        } else if (event && want && (flags & FLAG_INIT)) {
+            n_adv = (nh > Dm1) ? nh - Dm1 : 0;           // held or rejected: catch up inside the CTA-mates' event
+        }
+        if (event) {
+            T scratch[3] = { T(0), T(0), T(0) };
+            advance(&s, k - nh, n_adv, scratch, nullptr);
+            nh -= n_adv;
+        }
+        if (perform) {
+            ++n_corr;
+            Observation<T> obs;
+            correction_call<T, BIAS, DIRECT>(&s, P, tag, par_cold, &obs);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) a.st.aux[(6 + cc) * a.st.ld + i] = obs.q_tv_obs[cc];
+            hlen = nh + 1;                               // history before the corrected entry is erased (cpp:214-219)
+        }
+        if (exec) {
+            // cpp:240-257: the head prediction of tick k is implied; its (implied) input joins the history
+            ++nh; ++hlen;
+            if (perform) { upds = 0; flags |= FLAG_CORRECTED; }
+            else { upds += 1; flags &= ~FLAG_CORRECTED; }
+            flags |= FLAG_ACTIVE;
+            ++k;
+            if (k == next_fence) at_fence = true;
+        }
+    }
+    if (!live) return;
+
+    if ((flags & FLAG_READY) && pend_m >= 0) {
+        double tg[7];
+        in.tag_f64(a.in, a.ns, pend_m, tg);
+#pragma unroll
+        for (int cc = 0; cc < 7; ++cc) a.st.pend[cc * a.st.ld + i] = tg[cc];
+        a.st.pend[7 * a.st.ld + i] = a.in.tag_stamp[pend_m];
+    }
+    // checkpoint home (as far forward as any future correction allows), then the head (what the accessors read); the
+    // inputs of the entries in between go to ring slots 0 .. nh-1 for whoever continues from this state
+    int32_t hp = 0;
+    if (flags & FLAG_INIT) {
+        const int32_t n_c = (nh > Dm1) ? nh - Dm1 : 0;
+        T scratch[3] = { T(0), T(0), T(0) };
+        advance(&s, k - nh, n_c, scratch, nullptr);
+        nh -= n_c;
+        store_checkpoint<T>(a.st, i, s, P);
+        advance(&s, k - nh, nh, accel, a.st.ring + i);
+        store_filter<T>(a.st, i, s, P);
+        hp = (nh > 0) ? nh - 1 : 0;
+    }
+    a.st.flags[i] = flags;
+    a.st.upds[i] = upds;
+    a.st.nh[i] = nh; a.st.hpos[i] = hp; a.st.hlen[i] = hlen;
+    if (a.st.counts) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(a.st.counts + 0, (unsigned long long)(uint32_t)(int32_t)n_pred);
+        atomicAdd(a.st.counts + 1, (unsigned long long)n_corr);
+        if ((i & 31) == 0) atomicAdd(a.st.counts + 2, (unsigned long long)n_iter);
+        atomicAdd(a.st.counts + 4, (unsigned long long)n_sexec);
+#else
+        a.st.counts[0] += (uint32_t)(int32_t)n_pred;
+        a.st.counts[1] += n_corr;
+#endif
+    }
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) a.st.aux[cc * a.st.ld + i] = accel[cc];
+}
+
 // CTA-cooperative copy of the launch-wide constants into shared memory (whole 8-byte words; VOTE_WORDS and the
 // scratch sizes keep the destination 8-byte aligned)
 template <typename T> __device__ __forceinline__ void copy_consts(Consts<T> *dst, const Consts<T> &src)
@@ -1015,8 +1288,14 @@ __global__ void __launch_bounds__(BLOCK, 1) run_kernel(const __grid_constant__ R
 #endif
     // padding lanes still take part in the votes
 #ifndef QEKF_EXP8
-    if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
-    else run_filter<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    if constexpr (MR && SYNTH) {
+        if (a.st.hist_synth) run_filter_mrs<T, BIAS, DIRECT, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+        else run_filter_mr<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    } else if constexpr (MR) {
+        run_filter_mr<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    } else {
+        run_filter<T, BIAS, DIRECT, SYNTH, PF, PShared<T, N, BLOCK>, true>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
+    }
 #else
     if (MR) run_filter_mr<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);
     else run_filter<T, BIAS, DIRECT, SYNTH, PF>(a, i, P, scr + threadIdx.x, BLOCK, live, vbuf, csm);

@@ -73,17 +73,21 @@ QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
     z1 = r * s;
 }
 
-// six standard normals for (global filter id, stream, index)
-QEKF_FN void normals6(const NoiseSpec &ns, int64_t gid, uint32_t stream, uint32_t index, float z[6])
+// six standard normals for (seed, global filter id, stream, index)
+QEKF_FN void normals6(uint64_t seed, int64_t gid, uint32_t stream, uint32_t index, float z[6])
 {
     uint32_t w0[4], w1[4];
-    const uint32_t k0 = (uint32_t)ns.seed, k1 = (uint32_t)(ns.seed >> 32);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t g0 = (uint32_t)(uint64_t)gid, g1 = (uint32_t)((uint64_t)gid >> 32);
     philox4x32_10(index, stream, g0, g1, k0, k1, w0);
     philox4x32_10(index, stream + 1u, g0, g1, k0, k1, w1);
     box_muller(w0[0], w0[1], z[0], z[1]);
     box_muller(w0[2], w0[3], z[2], z[3]);
     box_muller(w1[0], w1[1], z[4], z[5]);
+}
+QEKF_FN void normals6(const NoiseSpec &ns, int64_t gid, uint32_t stream, uint32_t index, float z[6])
+{
+    normals6(ns.seed, gid, stream, index, z);
 }
 
 // the constant true IMU bias of a filter
@@ -117,15 +121,25 @@ QEKF_FN bool arrival_valid(const NoiseSpec &ns, int32_t step, int32_t priv_start
 }
 
 // noisy IMU sample of tick k:  clean + bias + sigma * n          (doubles; the caller narrows)
-QEKF_FN void synth_imu(const NoiseSpec &ns, int64_t gid, int64_t k, const double clean[6], const double bias[6], double u[6])
+// (the scalars of the noise model an IMU sample depends on; small enough to travel through a call in registers)
+struct ImuSynth {
+    uint64_t seed;
+    float sig_a, sig_w, sig_ba, sig_bw;
+};
+QEKF_FN void synth_imu(const ImuSynth &nz, int64_t gid, int64_t k, const double clean[6], const double bias[6], double u[6])
 {
     float z[6];
-    normals6(ns, gid, STREAM_IMU, (uint32_t)k, z);
+    normals6(nz.seed, gid, STREAM_IMU, (uint32_t)k, z);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        u[i] = clean[i] + bias[i] + (double)ns.sig_a * (double)z[i];
-        u[3 + i] = clean[3 + i] + bias[3 + i] + (double)ns.sig_w * (double)z[3 + i];
+        u[i] = clean[i] + bias[i] + (double)nz.sig_a * (double)z[i];
+        u[3 + i] = clean[3 + i] + bias[3 + i] + (double)nz.sig_w * (double)z[3 + i];
     }
+}
+QEKF_FN void synth_imu(const NoiseSpec &ns, int64_t gid, int64_t k, const double clean[6], const double bias[6], double u[6])
+{
+    const ImuSynth nz{ ns.seed, ns.sig_a, ns.sig_w, ns.sig_ba, ns.sig_bw };
+    synth_imu(nz, gid, k, clean, bias, u);
 }
 
 // Detection front-end, geometry: does at least one tag of the bundle project with all four corners strictly inside

@@ -98,6 +98,13 @@ struct qekf_handle {
     int32_t perm_len = 0, perm_lo = 0, perm_hi = 0;
     bool perm_on = true;             // QEKF_NO_PERM=1 disables it (A/B runs)
     int64_t perm_min_steps = 256;    // shortest replay that is reordered (QEKF_PERM_MIN_STEPS overrides)
+    // Delayed fusion: may a Monte-Carlo launch re-synthesise the IMU inputs of the history entries it finds instead of
+    // reading the ring?  Yes if no filter has an entry after its checkpoint (hist_clean: fresh, reset or rebased handle),
+    // or if they were all produced by Monte-Carlo launches of the same noise model and scenario ending where this one
+    // starts (hist_key).  Any other entry point that touches the histories clears both.
+    bool hist_clean = true, hist_key_valid = false, lazy_mr_on = true, lazy_now = false;     // QEKF_NO_LAZY_MR=1 disables the path (A/B runs)
+    uint64_t hist_key[6] = { 0, 0, 0, 0, 0, 0 };
+    int64_t hist_k_next = 0;
     // launch bookkeeping
     int64_t launches = 0;
     // mapping of the fused replay (qekf_set_mapping), where the kernels exist (FP64, single-rate): 2 = two role-specialised
@@ -120,7 +127,19 @@ template <typename T> DeviceState<T> dstate(const qekf_handle *h)
     s.pf_delay = h->pf_on ? h->pf_delay : nullptr;
     s.perm = nullptr;
     s.gid_perm = nullptr;
+    s.hist_synth = 0;
     return s;
+}
+
+// the delayed-fusion histories are about to be touched by something other than a Monte-Carlo launch
+void hist_touch(qekf_handle *h) { h->hist_clean = false; h->hist_key_valid = false; }
+void hist_emptied(qekf_handle *h) { h->hist_clean = true; h->hist_key_valid = false; }
+
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t hsh = 1469598103934665603ULL)
+{
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; ++i) { hsh ^= p[i]; hsh *= 1099511628211ULL; }
+    return hsh;
 }
 
 int block_of(const qekf_handle *h) { return h->precision == QEKF_FP64 ? BlockOf<double>::value : BlockOf<float>::value; }
@@ -229,6 +248,7 @@ int rebase_all(qekf_handle *h)
     if (!h->p.multirate_ekf || !h->xc) return QEKF_OK;
     if (h->precision == QEKF_FP64) CUDA_TRY(launch_rebase<double>(dstate<double>(h), h->np, h->stream));
     else CUDA_TRY(launch_rebase<float>(dstate<float>(h), h->np, h->stream));
+    hist_emptied(h);
     return QEKF_OK;
 }
 
@@ -295,6 +315,7 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
         // a reordered launch (qekf_run_monte_carlo has gathered the per-filter arrays into slot order): row j of every
         // array belongs to filter d_perm[j], which is what keys its noise
         a.st.gid_perm = h->in_slot_order ? h->d_perm : nullptr;
+        a.st.hist_synth = h->lazy_now ? 1 : 0;
         if (h->stats_acc && truth && h->stats_stride > 0) {
             a.stats.save = nullptr;
             a.stats.acc = h->stats_acc; a.stats.truth = truth;
@@ -643,6 +664,8 @@ int qekf_create(const qekf_params *p, int64_t n_filters, int device, int precisi
         if (e && coop_groups_available(atoi(e), p->est_bias && p->direct_orien_method)) h->coop_groups = atoi(e);
         e = getenv("QEKF_NO_PERM");
         if (e && atoi(e) != 0) h->perm_on = false;
+        e = getenv("QEKF_NO_LAZY_MR");
+        if (e && atoi(e) != 0) h->lazy_mr_on = false;
         e = getenv("QEKF_PERM_MIN_STEPS");
         if (e && atoll(e) > 0) h->perm_min_steps = atoll(e);
         e = getenv("QEKF_DUO_GROUPS");
@@ -823,6 +846,7 @@ int qekf_set_imu(qekf_handle *h, const double accel[3], const double gyro[3])
 
 static int deliver(qekf_handle *h, int force_init, int reinit_bias, int raise_ready = 1)
 {
+    if (h) hist_touch(h);
 #define CALL_DELIVER(T, B, D)                                                                                          \
     do {                                                                                                               \
         if (h->pf_on)                                                                                                  \
@@ -875,6 +899,7 @@ int qekf_initialize_state(qekf_handle *h, int reinit_bias)
 int qekf_tick(qekf_handle *h, const double accel[3], const double gyro[3], int tag_mode, const double tag_pos[3],
               const double tag_quat_xyzw[4], double tag_stamp, double t_curr, int n_out, double *records)
 {
+    if (h) hist_touch(h);
     if (!h || !accel || !gyro) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     if (tag_mode < 0 || tag_mode > 2 || (tag_mode != 0 && (!tag_pos || !tag_quat_xyzw)))
         return fail(QEKF_ERR_BAD_ARG, "bad tag_mode, or a tag without a pose");
@@ -912,6 +937,7 @@ int qekf_tick(qekf_handle *h, const double accel[3], const double gyro[3], int t
 
 int qekf_filter_update(qekf_handle *h, double t_curr)
 {
+    if (h) hist_touch(h);
     if (!h) return fail(QEKF_ERR_BAD_ARG, "handle is NULL");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -929,6 +955,7 @@ int qekf_filter_update(qekf_handle *h, double t_curr)
 
 int qekf_run(qekf_handle *h, const qekf_streams *s, int64_t k0, int64_t n_steps)
 {
+    if (h) hist_touch(h);
     if (!h || !s) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return QEKF_OK;
     if (k0 < 0 || n_steps < 0 || k0 + n_steps > s->T) return fail(QEKF_ERR_BAD_ARG, "tick range outside the stream");
@@ -1051,6 +1078,7 @@ int qekf_get_flags(qekf_handle *h, int64_t first, int64_t count, int32_t *flags6
 
 int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x16, const double *P)
 {
+    if (h) hist_touch(h);
     if (!range_ok(h, first, count) || !x16 || !P) return fail(QEKF_ERR_BAD_ARG, "bad range or NULL input");
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = store_rows(h, h->x, 16, first, count, x16);
@@ -1086,10 +1114,14 @@ int qekf_set_state(qekf_handle *h, int64_t first, int64_t count, const double *x
 namespace {
 
 struct ExportHeader {
-    char magic[8];                 // "QEKFCKP1"
+    char magic[8];                 // "QEKFCKP2"
     int32_t precision, nstates, multirate, ring_len, dmax, stats_bins, stats_stride, reserved;
     int64_t n, ld, total_bytes;
     double imu_latched[6];
+    // provenance of the delayed-fusion history entries (qekf_handle::hist_clean / hist_key)
+    int32_t hist_clean, hist_key_valid;
+    uint64_t hist_key[6];
+    int64_t hist_k_next;
     qekf_params p;
 };
 
@@ -1133,12 +1165,14 @@ int qekf_export_state(qekf_handle *h, void *buf, int64_t bytes)
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     ExportHeader hd;
     std::memset(&hd, 0, sizeof hd);
-    std::memcpy(hd.magic, "QEKFCKP1", 8);
+    std::memcpy(hd.magic, "QEKFCKP2", 8);
     hd.precision = h->precision; hd.nstates = h->nstates; hd.multirate = h->xc ? 1 : 0;
     hd.ring_len = h->ring_len; hd.dmax = h->dmax;
     hd.stats_bins = h->stats_acc ? h->stats_bins : 0; hd.stats_stride = h->stats_acc ? h->stats_stride : 0;
     hd.n = h->n; hd.ld = h->ld; hd.total_bytes = need;
     std::memcpy(hd.imu_latched, h->imu_latched, sizeof hd.imu_latched);
+    hd.hist_clean = h->hist_clean; hd.hist_key_valid = h->hist_key_valid; hd.hist_k_next = h->hist_k_next;
+    std::memcpy(hd.hist_key, h->hist_key, sizeof hd.hist_key);
     hd.p = h->p;
     unsigned char *out = static_cast<unsigned char *>(buf);
     std::memcpy(out, &hd, sizeof hd);
@@ -1156,7 +1190,7 @@ int qekf_import_state(qekf_handle *h, const void *buf, int64_t bytes)
     if (bytes < (int64_t)sizeof(ExportHeader)) return fail(QEKF_ERR_BAD_ARG, "blob is shorter than its header");
     ExportHeader hd;
     std::memcpy(&hd, buf, sizeof hd);
-    if (std::memcmp(hd.magic, "QEKFCKP1", 8) != 0) return fail(QEKF_ERR_BAD_ARG, "not a qekf_export_state blob");
+    if (std::memcmp(hd.magic, "QEKFCKP2", 8) != 0) return fail(QEKF_ERR_BAD_ARG, "not a qekf_export_state blob");
     if (hd.total_bytes > bytes) return fail(QEKF_ERR_BAD_ARG, "blob is truncated");
     if (hd.n != h->n || hd.ld != h->ld || hd.precision != h->precision || hd.nstates != h->nstates)
         return fail(QEKF_ERR_BAD_ARG, "blob was exported from a handle of another size, precision or est_bias");
@@ -1183,6 +1217,8 @@ int qekf_import_state(qekf_handle *h, const void *buf, int64_t bytes)
         off += s.bytes;
     }
     std::memcpy(h->imu_latched, hd.imu_latched, sizeof hd.imu_latched);
+    h->hist_clean = hd.hist_clean != 0; h->hist_key_valid = hd.hist_key_valid != 0; h->hist_k_next = hd.hist_k_next;
+    std::memcpy(h->hist_key, hd.hist_key, sizeof hd.hist_key);
     return QEKF_OK;
 }
 
@@ -1200,6 +1236,7 @@ static int stage_rows(qekf_handle *h, const double *host, int rows)
 
 int qekf_prediction_step(qekf_handle *h, const double *u)
 {
+    if (h) hist_touch(h);
     if (!h || !u) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, u, 6);
@@ -1221,6 +1258,7 @@ int qekf_prediction_step(qekf_handle *h, const double *u)
 
 int qekf_correction_step(qekf_handle *h, const double *tag_pose)
 {
+    if (h) hist_touch(h);
     if (!h || !tag_pose) return fail(QEKF_ERR_BAD_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = stage_rows(h, tag_pose, 7);
@@ -1373,7 +1411,27 @@ int qekf_run_monte_carlo(qekf_handle *h, const qekf_shared_streams *s, const qek
         rc = permute_state(h, true);
         if (rc) return rc;
     }
+    // delayed fusion: may this launch re-synthesise the history entries it finds (see qekf_handle::hist_clean)?
+    uint64_t key[6] = { 0, 0, 0, 0, 0, 0 };
+    bool regenerable = false;
+    if (h->p.multirate_ekf) {
+        key[0] = ns.seed; key[1] = (uint64_t)ns.gid0;
+        std::memcpy(&key[2], &ns.sig_a, 8);                 // sig_a, sig_w
+        std::memcpy(&key[3], &ns.sig_ba, 8);                // sig_ba, sig_bw
+        key[4] = s->on_device ? (uint64_t)(uintptr_t)s->imu_clean : fnv1a(s->imu_clean, (size_t)s->T * 6 * 8);
+        key[5] = (uint64_t)s->T ^ ((uint64_t)s->on_device << 62);
+        regenerable = h->hist_clean || (h->hist_key_valid && std::memcmp(key, h->hist_key, sizeof key) == 0 && k0 == h->hist_k_next);
+    }
+    h->lazy_now = regenerable && h->lazy_mr_on;
     rc = run_dispatch(h, in, k0, n_steps, m0, &ns, truth);
+    h->lazy_now = false;
+    if (h->p.multirate_ekf) {
+        // (either kernel leaves entries that are this noise model's samples of this scenario -- if the ones it found were)
+        h->hist_clean = false;
+        h->hist_key_valid = regenerable && rc == QEKF_OK;
+        std::memcpy(h->hist_key, key, sizeof key);
+        h->hist_k_next = k0 + n_steps;
+    }
     if (reorder) {
         const int rc2 = permute_state(h, false);
         if (!rc) rc = rc2;
@@ -1488,6 +1546,7 @@ int qekf_reset_filters(qekf_handle *h)
         CUDA_TRY(cudaMemsetAsync(h->hpos, 0, ld * sizeof(int32_t), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->hlen, 0, ld * sizeof(int32_t), h->stream));
     }
+    hist_emptied(h);
     return reset_cov(h, true);
 }
 
