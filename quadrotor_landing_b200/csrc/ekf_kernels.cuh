@@ -478,14 +478,16 @@ constexpr int SR_SCRATCH_INTS = 16;
 // (tests/host_core) can run the very same code against the oracle without a GPU; the product only ever
 // calls it from run_kernel.
 //
-// Time skew: every lane keeps its OWN tick index k.  The correction step costs 2.5x a prediction and fires
-// once per upd_per_meas ticks; lanes whose cadence is out of phase with their CTA-mates (a private tag
-// dropout, a rejected detection, a late initialisation) would make the warps execute it almost every tick
-// with a handful of active lanes.  Instead, a lane whose tick would correct while only a minority of the
-// CTA wants to holds that tick back (it simply does not execute this iteration) until a strict majority
-// wants to correct, or its patience (upd_per_meas - 1 iterations) runs out.  Held lanes are then served
-// together and stay aligned from there on.  Filters are independent, so executing a filter's tick a few
-// iterations later changes nothing in its arithmetic: results are bit-identical to the unskewed loop.
+// Event-driven: every lane keeps its OWN tick index k and runs the ticks that need no decision of the CTA -- tag
+// callbacks, predictions, bookkeeping -- in an inner loop without calls, votes or barriers (round 2; the loop used to
+// iterate over ticks with one CTA-wide vote and barrier per tick, and the ~250 instructions of sequencing per tick plus
+// the values ptxas parked in local memory around the call sites were a fifth of the time).  A lane leaves the inner
+// loop when the prediction of a tick whose measurement gate is open is done, at a sampling boundary, or at the end of
+// the launch; only there the CTA meets.  The correction step (2.5x a prediction, once per upd_per_meas ticks) is then
+// executed once for the whole CTA: lanes whose cadence is out of phase with their CTA-mates (a private tag dropout, a
+// rejected detection, a late initialisation) arrive after different numbers of ticks and are corrected together, at
+// their own tick indices.  Filters are independent, so when a filter's tick is executed changes nothing in its
+// arithmetic: results are bit-identical to a loop that walks all filters tick by tick.
 // Statistics fence: a lane that has finished a sampling tick waits until every lane of the CTA has, then all
 // sample together (one execution of the sampling code per stride; the time skew is back to zero).
 // `live` = false marks the padding lanes of a ragged last CTA (they only take part in the votes).
@@ -536,38 +538,78 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
     m = a.m0;
     next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
     pend_m = -1;                       // index of the latched arrival; -1 = latched pose lives in st.pend
-    held = 0;                          // iterations this lane has held its correction tick back
-    bool at_fence = false;             // finished a sampling tick; waiting for the warp to catch up
+    held = 0;                          // iterations this lane has held its correction back
+    bool at_fence = false;             // finished a sampling tick; waiting for the CTA to catch up
     const bool do_stats = SYNTH && a.stats.acc != nullptr;
     const int32_t patience = c.limit_measurement_freq ? (c.upd_per_meas - 1) : 0;
     // the next sampling boundary (a multiple of the stride): every lane of the CTA stops there until all have arrived, so
     // it is the same for all of them and moves on when the sample is taken -- no k % stride on the per-tick path
     int32_t next_fence = do_stats ? (int32_t)((a.k0 / a.stats.stride + 1) * a.stats.stride) : INT32_MAX;
+    bool predicted = false;            // the prediction of tick k has run; the tick waits for its correction
 
     cta_vote_init(vbuf);
     for (uint32_t iter = 0;; ++iter) {
-        const bool active = (k < k_end) && !at_fence;
-
-        // ---- AprilTagSubCallback for the arrival scheduled at tick k (node.cpp:153-176); idempotent ----
-        if (active && k == next_tag_step) {
-            if (in.valid(a.in, a.ns, m, (int32_t)k)) {
-                pend_m = m;
-                flags |= FLAG_READY;
-                if (!(flags & FLAG_INIT)) {
-                    T tag0[7];
-                    in.tag(a.in, a.ns, m, tag0);
-                    initialize_state<T, BIAS>(s, P, tag0, par, false);
-                    flags |= FLAG_INIT;
+        // ---- The ticks that need no decision of the CTA: tag callback (node.cpp:153-176), prediction (cpp:240-249),
+        //      bookkeeping -- a loop of its own, without calls, votes or barriers, whose state lives in registers.  A lane
+        //      leaves it with the prediction of a tick whose measurement gate is open (cpp:147) done and its correction
+        //      pending, at a sampling boundary, or at the end of the launch; the CTA meets (one vote, one barrier) only
+        //      there.  Lanes whose tick indices differ (private dropouts, late initialisation) leave after different
+        //      numbers of ticks and are corrected together, at their own ticks: filters are independent, so when a
+        //      filter's tick is executed changes nothing in its arithmetic. ----
+        bool want = predicted;
+        if (k < k_end && !at_fence && !predicted) {
+            int32_t kk = k, up = upds, fl = flags, nts = next_tag_step, np_run = 0;
+            for (;;) {
+                if (kk == nts) {
+                    const int32_t mm = m;
+                    if (in.valid(a.in, a.ns, mm, kk)) {
+                        pend_m = mm;
+                        fl |= FLAG_READY;
+                        if (!(fl & FLAG_INIT)) {
+                            T tag0[7];
+                            in.tag(a.in, a.ns, mm, tag0);
+                            initialize_state<T, BIAS>(s, P, tag0, par, false);
+                            fl |= FLAG_INIT;
+                        }
+                    }
+                    m = mm + 1;
+                    nts = (mm + 1 < a.in.M) ? a.in.tag_step[mm + 1] : INT32_MAX;
                 }
+                const bool init = (fl & FLAG_INIT) != 0;
+                const bool gate = init && (fl & FLAG_READY) && (!c.limit_measurement_freq || (up + 1) >= c.upd_per_meas);
+                if (init) {
+                    T u[6];
+                    if (SYNTH) {
+                        // the clean sample is shared by all filters (L1 / L2 resident) and is fetched here, at its use: the
+                        // Philox rounds of the noise cover the load
+                        double raw[6], tb[6], ud[6];
+                        in.raw_imu(a.in, kk, raw);
+                        true_bias_now(tb);
+                        synth_imu(a.ns, in.gid, kk, raw, tb, ud);
+#pragma unroll
+                        for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
+                    } else {
+                        in.imu(a.ns, kk, un, u);
+                    }
+                    prediction_step<T, BIAS>(s, P, u, par, accel);
+                    ++np_run;
+                }
+                if (gate) { want = true; break; }        // tick kk: predicted, correction pending
+                if (init) {
+                    up += 1;
+                    fl = (fl & ~FLAG_CORRECTED) | FLAG_ACTIVE;
+                }
+                ++kk;
+                if (!SYNTH && kk < k_end) in.raw_imu(kk, un);
+                if (kk == next_fence) { at_fence = true; break; }          // tick kk-1 was a sampling tick
+                if (kk >= k_end) break;
             }
-            ++m;
-            next_tag_step = (m < a.in.M) ? a.in.tag_step[m] : INT32_MAX;
+            k = kk; upds = up; flags = fl; next_tag_step = nts;
+            n_pred += np_run;
+            predicted = want;
         }
-
-        // ---- would tick k fuse a measurement?  (gate of cpp:147; no side effects yet) ----
+        const bool active = (k < k_end) && !at_fence;
         const int32_t fl0 = flags;
-        const bool want = active && (fl0 & FLAG_INIT) && (fl0 & FLAG_READY) &&
-                          (!c.limit_measurement_freq || (upds + 1) >= c.upd_per_meas);
         const CtaVote v = cta_vote(vbuf, iter, active, want, want && held >= patience, at_fence || k >= k_end, at_fence);
         if (v.active == 0 && v.at_fence == 0) break;     // every lane of the CTA has finished
         ++n_iter;
@@ -581,15 +623,18 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
             at_fence = false;
             next_fence += a.stats.stride;
         }
+        // (every active lane is waiting for a correction here, so the wanting lanes are always a majority of the active
+        //  ones; the hold logic stays for CTAs of the per-tick interface, where it is a no-op too)
         bool serve = true;
         if (v.want != 0) serve = (2 * v.want > v.active) || v.out_of_patience;
-        if (want && !serve) ++held;                      // hold tick k back; nothing has been consumed
-        const bool exec = active && !(want && !serve) && (fl0 & FLAG_INIT);
+        if (want && !serve) ++held;
 
-        // ---- consume the measurement, corner-margin gate (cpp:150-186) ----
-        bool perform = false;
-        T tag[7];
-        if (exec && want) {
+#if defined(__CUDA_ARCH__) && defined(QEKF_DIAG_EVENTS)
+        if (__ballot_sync(0xffffffffu, want && serve) != 0u) ++n_cev;    // diagnostics: iterations in which this warp runs the correction
+#endif
+        if (want && serve) {
+            // ---- consume the measurement, corner-margin gate (cpp:150-186), single-rate correction (cpp:265-279) ----
+            T tag[7];
             if (pend_m >= 0) {
                 in.tag(a.in, a.ns, pend_m, tag);
             } else {
@@ -597,30 +642,8 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
                 for (int cc = 0; cc < 7; ++cc) tag[cc] = (T)a.st.pend[cc * a.st.ld + i];
             }
             flags &= ~FLAG_READY;
-            perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
+            const bool perform = c.corner_margin_enbl ? corner_gate<T>(tag, c) : true;
             held = 0;
-        }
-
-#if defined(__CUDA_ARCH__) && defined(QEKF_DIAG_EVENTS)
-        if (__ballot_sync(0xffffffffu, perform) != 0u) ++n_cev;    // diagnostics: iterations in which this warp runs the correction
-#endif
-        if (exec) {                                      // else: held, finished, or filter_update returns early (cpp:129-130)
-            // ---- prediction (cpp:240-249), then single-rate correction (cpp:265-279) ----
-            T u[6];
-            if (SYNTH) {
-                // the clean sample is shared by all filters (L1 / L2 resident) and is fetched here, at its use: the Philox
-                // rounds of the noise cover the load, and nothing has to be carried across the iteration
-                double raw[6], tb[6], ud[6];
-                in.raw_imu(a.in, k, raw);
-                true_bias_now(tb);
-                synth_imu(a.ns, in.gid, k, raw, tb, ud);
-#pragma unroll
-                for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
-            } else {
-                in.imu(a.ns, k, un, u);
-            }
-            prediction_step<T, BIAS>(s, P, u, par, accel);
-            ++n_pred;
             if (perform) {
                 ++n_corr;
                 Observation<T> obs;
@@ -640,8 +663,7 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
                 flags &= ~FLAG_CORRECTED;
             }
             flags |= FLAG_ACTIVE;
-        }
-        if (active && !(want && !serve)) {
+            predicted = false;
             ++k;
             if (!SYNTH && k < k_end) in.raw_imu(k, un);
             if (k == next_fence) at_fence = true;        // tick k-1 was a sampling tick

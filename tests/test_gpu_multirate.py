@@ -146,3 +146,63 @@ def test_multirate_monte_carlo_matches_explicit_path_and_statistics():
     assert np.array_equal(stats[:, 16], ref[:, 16])
     assert norm_rel(stats[:, 0:16], ref[:, 0:16]) < TOL and norm_rel(stats[:, 19], ref[:, 19]) < TOL
     b.close(); b2.close()
+
+
+def _mc_noise(first=0):
+    n = q.default_noise()
+    n.seed = 4711
+    n.first_global_id = first
+    n.dropout_k0, n.dropout_k1 = 500, 640
+    n.rand_dropout_len, n.rand_dropout_lo, n.rand_dropout_hi = 160, 100, 1300
+    return n
+
+
+@pytest.mark.parametrize("dynamic,sweep,precision", [(0, 0, 64), (1, 0, 64), (1, 1, 64), (1, 0, 32)])
+def test_resynthesised_history_equals_ring_history(monkeypatch, dynamic, sweep, precision):
+    """Monte-Carlo launches with delayed fusion re-synthesise the IMU inputs of the history entries (no ring, no light
+    ticks: run_filter_mrs); QEKF_NO_LAZY_MR=1 keeps the ring-based loop.  Same arithmetic on the same inputs: every
+    accessor bit-identical, over chunked launches whose cuts fall between corrections."""
+    p = rotors_params(q.default_params(), multirate=True, dynamic_delay=bool(dynamic))
+    scn = delayed_scenario(p, 0.042 if dynamic else 0.030, seconds=8.0)
+    N = 1500
+    out = []
+    for env in ({"QEKF_NO_LAZY_MR": "1"}, {}):
+        monkeypatch.delenv("QEKF_NO_LAZY_MR", raising=False)
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        b = q.BatchEKF(p, N, precision=precision)
+        if sweep:
+            for field, v in sweep_values(np.random.default_rng(3), p, N, True).items():
+                b.set_filter_params(field, v)
+        b.stats_configure(16, 100)
+        for k0, n in ((0, 611), (611, 2), (613, 987)):
+            b.run_monte_carlo(scn, _mc_noise(), k0, n)
+        out.append(([b.state(), b.cov(), b.aux(), b.flags()], b.stats(), b.step_counts()))
+        b.close()
+    (ring, ring_stats, ring_counts), (lazy, lazy_stats, lazy_counts) = out
+    for x, y in zip(ring, lazy):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert lazy_counts[1] == ring_counts[1] and lazy_counts[1] > 100 * N
+    assert np.array_equal(lazy_stats[:, 16:19], ring_stats[:, 16:19])
+    assert np.allclose(lazy_stats, ring_stats, rtol=1e-11, atol=0)
+
+
+def test_monte_carlo_history_hands_over_to_the_other_entry_points():
+    """A Monte-Carlo launch leaves a history the ring-based paths can continue from (its epilogue writes the pending
+    entries' inputs to the ring), and a handle whose history came from explicit streams is not re-synthesised: explicit
+    run -> Monte-Carlo launch -> explicit run, against the oracle replaying the same inputs end to end."""
+    p = rotors_params(q.default_params(), multirate=True, dynamic_delay=True)
+    scn = delayed_scenario(p, 0.042, seconds=8.0)
+    N, T = 96, 1500
+    noise = _mc_noise(first=1000)
+    b = q.BatchEKF(p, N)
+    st = b.synthesize_streams(scn, noise, 0, N)       # the realisation as explicit streams: what the oracle replays
+    args = (st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    ob = orc.Batch(orc.params_from(p), N)
+    ob.run(0, T, *args)
+    b.run(0, 403, *args)                              # explicit streams (history entries live in the ring)
+    b.run_monte_carlo(scn, noise, 403, 300)           # must read them from the ring
+    b.run_monte_carlo(scn, noise, 703, 300)           # (still the ring: entries from before the explicit run may be pending)
+    b.run(1003, T - 1003, *args)                      # continues from the ring the Monte-Carlo launch left behind
+    compare(b, ob)
+    b.close()
