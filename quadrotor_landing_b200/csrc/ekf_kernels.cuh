@@ -1207,9 +1207,29 @@ QEKF_FN void run_filter_mrs(const RunArgs<T> &a, const int64_t i_in, PS &P, int3
             n_adv = (nh > Dm1) ? nh - Dm1 : 0;           // held or rejected: catch up inside the CTA-mates' event
         }
         if (event) {
-            T scratch[3] = { T(0), T(0), T(0) };
-            advance(&s, k - nh, n_adv, scratch, nullptr);
-            nh -= n_adv;
+            // the replay before a delayed correction, inlined: the one place where predictions run in bulk (the calls of
+            // `advance` serve the sampling and the epilogue).  A loop without calls on a copy that never leaves registers.
+            if (n_adv > 0) {
+                Nominal<T> sl = s;
+                T scratch[3] = { T(0), T(0), T(0) };
+                const int32_t t0 = k - nh;
+                for (int32_t j = 0; j < n_adv; ++j) {
+                    T u[6];
+                    {
+                        double raw[6], tb[6], ud[6];
+                        in.raw_imu(a.in, (int64_t)(t0 + j), raw);
+#pragma unroll
+                        for (int cc = 0; cc < 6; ++cc) tb[cc] = (double)(cc < 3 ? nz.sig_ba : nz.sig_bw) * (double)bz[cc * scr_stride];
+                        synth_imu(nz, in.gid, (int64_t)(t0 + j), raw, tb, ud);
+#pragma unroll
+                        for (int cc = 0; cc < 6; ++cc) u[cc] = (T)ud[cc];
+                    }
+                    prediction_step<T, BIAS>(sl, P, u, par, scratch);
+                }
+                s = sl;
+                n_pred += n_adv;
+                nh -= n_adv;
+            }
         }
         if (perform) {
             ++n_corr;
