@@ -647,11 +647,9 @@ QEKF_FN void run_filter(const RunArgs<T> &a, const int64_t i_in, PS &P, int32_t 
             if (perform) {
                 ++n_corr;
                 Observation<T> obs;
-                {
-                    Nominal<T> tmp = s;
-                    correction_call<T, BIAS, DIRECT>(&tmp, P, tag, par_cold, &obs);
-                    s = tmp;
-                }
+                // inlined: behind a call (as it was while the loop iterated over ticks, to keep its ~120 live doubles out of
+                // the per-tick register allocation) everything the inner loop carries was spilled around it: 6.66e9 -> 7.09e9
+                correction_step<T, BIAS, DIRECT>(s, P, tag, par, obs);
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
@@ -1234,7 +1232,11 @@ QEKF_FN void run_filter_mrs(const RunArgs<T> &a, const int64_t i_in, PS &P, int3
         if (perform) {
             ++n_corr;
             Observation<T> obs;
-            correction_call<T, BIAS, DIRECT>(&s, P, tag, par_cold, &obs);
+            {
+                Nominal<T> sl = s;                       // (inlined on a copy that never leaves registers, like the replay)
+                correction_step<T, BIAS, DIRECT>(sl, P, tag, par, obs);
+                s = sl;
+            }
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) a.st.aux[(3 + cc) * a.st.ld + i] = obs.r_t_vt_obs[cc];
 #pragma unroll
