@@ -421,9 +421,14 @@ def run_ours(args):
         # NCCL's own log (communicator init: "... nranks N ...") is evidence the driver wants, so it is not silenced: it
         # is on at INFO for the INIT subsystem unless the environment already says otherwise, and reaches stderr with
         # everything else that is written to fd 1 (claim_stdout).
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (the GPU boxes run with NCCL_DEBUG=VERSION, which prints the banner only; INFO is a superset of it)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            print("[bench] torch.distributed backend nccl: world size %d (one rank per GPU), NCCL %s" % (
+                dist.get_world_size(), ".".join(str(v) for v in torch.cuda.nccl.version())), file=sys.stderr, flush=True)
 
     N = args.filters
     if args.scaling == "strong":
