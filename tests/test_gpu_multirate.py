@@ -157,12 +157,13 @@ def _mc_noise(first=0):
     return n
 
 
-@pytest.mark.parametrize("dynamic,sweep,precision", [(0, 0, 64), (1, 0, 64), (1, 1, 64), (1, 0, 32)])
-def test_resynthesised_history_equals_ring_history(monkeypatch, dynamic, sweep, precision):
+@pytest.mark.parametrize("dynamic,sweep,precision,est_bias,direct", [(0, 0, 64, 1, 1), (1, 0, 64, 1, 1), (1, 1, 64, 1, 1),
+                                                                     (1, 0, 32, 1, 1), (1, 0, 64, 0, 0), (0, 1, 64, 1, 0)])
+def test_resynthesised_history_equals_ring_history(monkeypatch, dynamic, sweep, precision, est_bias, direct):
     """Monte-Carlo launches with delayed fusion re-synthesise the IMU inputs of the history entries (no ring, no light
     ticks: run_filter_mrs); QEKF_NO_LAZY_MR=1 keeps the ring-based loop.  Same arithmetic on the same inputs: every
     accessor bit-identical, over chunked launches whose cuts fall between corrections."""
-    p = rotors_params(q.default_params(), multirate=True, dynamic_delay=bool(dynamic))
+    p = rotors_params(q.default_params(), multirate=True, dynamic_delay=bool(dynamic), est_bias=est_bias, direct=direct)
     scn = delayed_scenario(p, 0.042 if dynamic else 0.030, seconds=8.0)
     N = 1500
     out = []
