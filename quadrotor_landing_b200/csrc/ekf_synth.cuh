@@ -58,8 +58,20 @@ QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
 {
     const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), never 0
     const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
     float s, c;
+#ifdef __CUDA_ARCH__
+    // r = sqrt(-2 ln u1) from the SFU (lg2.approx, sqrt.approx) instead of logf + sqrtf (41 -> ~15 instructions per pair,
+    // the largest non-FP64 item of the tick).  lg2.approx is accurate to 2^-22 relative, or absolute on (0.5, 2); what
+    // matters is dr = d(ln u1) / r, so for u1 > 15/16, where r gets small, -ln u1 comes from its series in t = 1 - u1
+    // (exact in float; remainder t^6 / 6 <= 1.6e-7 relative).  r is then within ~1e-6 of the libm value everywhere.
+    const float t = 1.0f - u1;
+    const float ser = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+    const float nl = (t < 0.0625f) ? ser : -0.69314718f * __log2f(u1);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(2.0f * nl));
+#else
+    const float r = sqrtf(-2.0f * logf(u1));
+#endif
 #ifdef __CUDA_ARCH__
     // the SFU's sin / cos (absolute error < 7e-7 on [0, 2 pi): a relative 7e-7 of a noise sample) instead of sincospif's
     // range reduction and two polynomials: 6 instructions per pair instead of 35, on the per-tick path of every filter
