@@ -207,3 +207,30 @@ def test_monte_carlo_history_hands_over_to_the_other_entry_points():
     b.run(1003, T - 1003, *args)                      # continues from the ring the Monte-Carlo launch left behind
     compare(b, ob)
     b.close()
+
+
+@pytest.mark.parametrize("multirate", [0, 1])
+def test_monte_carlo_without_frequency_gate_equals_explicit_replay(multirate):
+    """limit_measurement_freq = 0: every valid detection is fused at its arrival tick (cpp:147), so the event-driven
+    loops stop at every arrival instead of every upd_per_meas ticks.  The Monte-Carlo launch (delayed fusion: no ring)
+    must equal, bit for bit, the explicit-stream replay of its own dumped realisation, and the oracle to 1e-9."""
+    p = rotors_params(q.default_params(), multirate=bool(multirate), dynamic_delay=bool(multirate))
+    p.limit_measurement_freq = 0
+    p.corner_margin_enbl = 0
+    scn = delayed_scenario(p, 0.060 if multirate else 0.0, seconds=6.0)
+    N = 200
+    noise = _mc_noise(first=77)
+    b = q.BatchEKF(p, N)
+    b.run_monte_carlo(scn, noise, 0, 500)
+    b.run_monte_carlo(scn, noise, 500, scn.T - 500)
+    st = b.synthesize_streams(scn, noise, 0, N)
+    args = (st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    b2 = q.BatchEKF(p, N)
+    b2.run(0, scn.T, *args)
+    for x, y in ((b.state(), b2.state()), (b.cov(), b2.cov()), (b.aux(), b2.aux()), (b.flags(), b2.flags())):
+        assert np.array_equal(x, y, equal_nan=True)
+    ob = orc.Batch(orc.params_from(p), N)
+    ob.run(0, scn.T, *args)
+    compare(b, ob)
+    assert ob.counts()[1] > 100 * N
+    b.close(); b2.close()
