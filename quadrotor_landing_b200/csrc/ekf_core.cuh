@@ -106,6 +106,18 @@ template <typename T> struct Nominal {
 // ------------------------------------------------------------------------------------------------
 enum { PF_Q = 0, PF_RA = 12, PF_RC = 15, PF_RAS = 21, PF_D = 27, PF_CVC = 36, PF_RVCV = 45, PF_QVC = 48, PF_DIM = 52 };
 
+// per-filter parameter tables are never written by a kernel that reads them: non-coherent loads, which the compiler may
+// hoist out of the replay loops and merge (a plain load through a generic pointer has to be re-issued after every store
+// to the covariance, which it cannot prove to be shared memory)
+template <typename T> QEKF_FN T ld_ro(const T *p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 template <typename T> struct ParU {
     const Consts<T> &c;
     QEKF_FN T Q(int i) const { return c.Q[i]; }
@@ -131,16 +143,16 @@ template <typename T> struct ParF {
     const T *t;          // this filter's column of the [PF_DIM][ld] table
     const double *dl;    // this filter's column of the [2][ld] delay table (measurement_delay, dyn offset)
     int64_t ld;
-    QEKF_FN T Q(int i) const { return t[(PF_Q + i) * ld]; }
-    QEKF_FN T Ra(int i) const { return t[(PF_RA + i) * ld]; }
-    QEKF_FN T RC(int i) const { return t[(PF_RC + i) * ld]; }
-    QEKF_FN T RA(int i) const { return t[(PF_RAS + i) * ld]; }
-    QEKF_FN T D(int i) const { return t[(PF_D + i) * ld]; }
-    QEKF_FN T C_vc(int i) const { return t[(PF_CVC + i) * ld]; }
-    QEKF_FN T r_v_cv(int i) const { return t[(PF_RVCV + i) * ld]; }
-    QEKF_FN T q_vc(int i) const { return t[(PF_QVC + i) * ld]; }
-    QEKF_FN double meas_delay() const { return dl[0]; }
-    QEKF_FN double dyn_offset() const { return dl[ld]; }
+    QEKF_FN T Q(int i) const { return ld_ro(t + (PF_Q + i) * ld); }
+    QEKF_FN T Ra(int i) const { return ld_ro(t + (PF_RA + i) * ld); }
+    QEKF_FN T RC(int i) const { return ld_ro(t + (PF_RC + i) * ld); }
+    QEKF_FN T RA(int i) const { return ld_ro(t + (PF_RAS + i) * ld); }
+    QEKF_FN T D(int i) const { return ld_ro(t + (PF_D + i) * ld); }
+    QEKF_FN T C_vc(int i) const { return ld_ro(t + (PF_CVC + i) * ld); }
+    QEKF_FN T r_v_cv(int i) const { return ld_ro(t + (PF_RVCV + i) * ld); }
+    QEKF_FN T q_vc(int i) const { return ld_ro(t + (PF_QVC + i) * ld); }
+    QEKF_FN double meas_delay() const { return ld_ro(dl); }
+    QEKF_FN double dyn_offset() const { return ld_ro(dl + ld); }
     QEKF_FN T dT() const { return c.dT; }
     QEKF_FN T g(int i) const { return c.g[i]; }
     QEKF_FN T ab_static(int i) const { return c.ab_static[i]; }
@@ -195,16 +207,16 @@ template <typename T> struct ParFS {
     const double *dl;
     int64_t ld;
     __device__ __forceinline__ T at(uint32_t off, int i) const { return lds_at<T>(base + off + (uint32_t)i * (uint32_t)sizeof(T)); }
-    __device__ __forceinline__ T Q(int i) const { return t[(PF_Q + i) * ld]; }
-    __device__ __forceinline__ T Ra(int i) const { return t[(PF_RA + i) * ld]; }
-    __device__ __forceinline__ T RC(int i) const { return t[(PF_RC + i) * ld]; }
-    __device__ __forceinline__ T RA(int i) const { return t[(PF_RAS + i) * ld]; }
-    __device__ __forceinline__ T D(int i) const { return t[(PF_D + i) * ld]; }
-    __device__ __forceinline__ T C_vc(int i) const { return t[(PF_CVC + i) * ld]; }
-    __device__ __forceinline__ T r_v_cv(int i) const { return t[(PF_RVCV + i) * ld]; }
-    __device__ __forceinline__ T q_vc(int i) const { return t[(PF_QVC + i) * ld]; }
-    __device__ __forceinline__ double meas_delay() const { return dl[0]; }
-    __device__ __forceinline__ double dyn_offset() const { return dl[ld]; }
+    __device__ __forceinline__ T Q(int i) const { return ld_ro(t + (PF_Q + i) * ld); }
+    __device__ __forceinline__ T Ra(int i) const { return ld_ro(t + (PF_RA + i) * ld); }
+    __device__ __forceinline__ T RC(int i) const { return ld_ro(t + (PF_RC + i) * ld); }
+    __device__ __forceinline__ T RA(int i) const { return ld_ro(t + (PF_RAS + i) * ld); }
+    __device__ __forceinline__ T D(int i) const { return ld_ro(t + (PF_D + i) * ld); }
+    __device__ __forceinline__ T C_vc(int i) const { return ld_ro(t + (PF_CVC + i) * ld); }
+    __device__ __forceinline__ T r_v_cv(int i) const { return ld_ro(t + (PF_RVCV + i) * ld); }
+    __device__ __forceinline__ T q_vc(int i) const { return ld_ro(t + (PF_QVC + i) * ld); }
+    __device__ __forceinline__ double meas_delay() const { return ld_ro(dl); }
+    __device__ __forceinline__ double dyn_offset() const { return ld_ro(dl + ld); }
     __device__ __forceinline__ T dT() const { return at(QEKF_CS_OFF(dT), 0); }
     __device__ __forceinline__ T g(int i) const { return at(QEKF_CS_OFF(g), i); }
     __device__ __forceinline__ T ab_static(int i) const { return at(QEKF_CS_OFF(ab_static), i); }
