@@ -15,7 +15,10 @@ namespace qekf {
 #ifdef QEKF_EXP8   // timing experiment only (results are wrong): 8 warps, the last 15 packed covariance elements aliased
 template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 384 : 256; };
 #else
-template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? 384 : 224; };
+#ifndef QEKF_FP32_BLOCK
+#define QEKF_FP32_BLOCK 384
+#endif
+template <typename T> struct BlockOf { static constexpr int value = (sizeof(T) == 4) ? QEKF_FP32_BLOCK : 224; };
 #endif
 
 template <typename T, bool BIAS, bool DIRECT, bool SYNTH, bool MR, bool PF>
