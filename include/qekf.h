@@ -121,12 +121,14 @@ int64_t qekf_num_filters(const qekf_handle *h);
  * qekf_set_stream adopts a caller stream (a cudaStream_t passed as void*). */
 /* How the fused replay (qekf_run, qekf_run_monte_carlo) maps filters onto the GPU (FP64 single-rate handles; other
  * handles use one thread per filter whatever is set here).
- *   lanes_per_filter = 2 (default): two role-specialised warps per 32 filters -- one owns the (dr,dv,dth) core of the
- *       covariance and the measurement update, the other the nominal state, the noise and the bias columns;
- *   lanes_per_filter = 3: three lanes per filter, each owning one column of every 3x3 covariance block;
- *   lanes_per_filter = 1: one thread per filter.
- * groups: 32-filter groups per CTA (0 = the build's default).  Results of the mappings agree to rounding (~1e-15), all
- * within the 1e-9 bar against relative_pose_EKF.cpp:127-502. */
+ *   lanes_per_filter = 1 (default): one thread per filter -- the fastest mapping by a factor of two to three
+ *       (profiles/r2_04_mappings.md);
+ *   lanes_per_filter = 2: two role-specialised warps per 32 filters -- one owns the (dr,dv,dth) core of the covariance
+ *       and the measurement update, the other the nominal state, the noise and the bias columns;
+ *   lanes_per_filter = 3: three lanes per filter, each owning one column of every 3x3 covariance block.
+ * The cooperative mappings are kept as measured alternatives.  groups: 32-filter groups per CTA (0 = the build's
+ * default).  Results of the mappings agree to rounding (~1e-15), all within the 1e-9 bar against
+ * relative_pose_EKF.cpp:127-502. */
 int qekf_set_mapping(qekf_handle *h, int lanes_per_filter, int groups);
 int qekf_set_stream(qekf_handle *h, void *cuda_stream);
 int qekf_sync(qekf_handle *h);

@@ -74,8 +74,9 @@ class BatchEKF:
         assert v.shape[-1] == self.N
         check(self._L.qekf_set_filter_params(self._h, int(field), _dp(v)))
 
-    def set_mapping(self, lanes_per_filter: int = 2, groups: int = 0):
-        """2 = two role-specialised warps per 32 filters, 3 = three lanes per filter, 1 = one thread per filter (FP64 single-rate handles); groups: 32-filter groups per CTA."""
+    def set_mapping(self, lanes_per_filter: int = 1, groups: int = 0):
+        """1 = one thread per filter (default, fastest), 2 = two role-specialised warps per 32 filters, 3 = three lanes per
+        filter (FP64 single-rate handles); groups: 32-filter groups per CTA."""
         nat.check(self._L.qekf_set_mapping(self._h, int(lanes_per_filter), int(groups)))
 
     def set_stream(self, cuda_stream: int):
