@@ -165,11 +165,13 @@ class HostBatch:
     def history_length(self):
         return self._history()["hlen"].copy() if self.p.multirate_ekf else (self.flags & 1)
 
-    def run_mc(self, scn, noise, k0=0, n_steps=None, stats=None, stride=0):
+    def run_mc(self, scn, noise, k0=0, n_steps=None, stats=None, stride=0, lazy=False):
         """Monte-Carlo replay (shared clean scenario + per-filter noise).  stats: array [32][n_bins][20] or None."""
         n_steps = scn.T - k0 if n_steps is None else n_steps
         imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
         step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+        if self.p.multirate_ekf or self.pf is not None:
+            return self._run_mc_ext(scn, noise, k0, n_steps, stats, stride, lazy)
         L = lib(self.prec)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.hc_run_mc.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, dp,
@@ -180,6 +182,31 @@ class HostBatch:
                     step.ctypes.data_as(ip), _dp(pose), _dp(stamp), _dp(truth), C.byref(noise), sp, nb, int(stride),
                     float(scn.spec.t_start), _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend),
                     self.flags.ctypes.data_as(ip), self.upds.ctypes.data_as(ip))
+
+    def _run_mc_ext(self, scn, noise, k0, n_steps, stats, stride, lazy):
+        """Monte-Carlo replay with delayed fusion / per-filter overrides; lazy: re-synthesise the history inputs
+        (run_filter_mrs) instead of reading the ring."""
+        imu = _f64(scn.imu_clean); pose = _f64(scn.tag_pose_clean); stamp = _f64(scn.tag_stamp); truth = _f64(scn.truth)
+        step = np.ascontiguousarray(scn.tag_step, dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        i32 = lambda a: a.ctypes.data_as(ip)
+        L = lib(self.prec)
+        L.hc_run_mc_ext.argtypes = ([C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int64, ip, dp, dp, dp,
+                                     C.c_void_p, dp, C.c_int32, C.c_int32, C.c_double] + [dp] * 4 + [ip] * 2 + [dp] * 3 +
+                                    [ip] * 3 + [C.c_int32, C.c_int32] + [dp] * 5 + [C.c_int])
+        if self.p.multirate_ekf:
+            h = self._history()
+            hist = [_dp(h["xc"]), _dp(h["Pc"]), _dp(h["ring"]), i32(h["nh"]), i32(h["hpos"]), i32(h["hlen"]),
+                    h["ring_len"], h["dmax"]]
+        else:
+            hist = [None, None, None, None, None, None, 0, 1]
+        pf = [_dp(a) for a in self.pf] if self.pf is not None else [None] * 5
+        sp = _dp(stats) if stats is not None else None
+        nb = stats.shape[1] if stats is not None else 0
+        L.hc_run_mc_ext(C.byref(self.p), int(self.prec), self.N, int(k0), int(n_steps), _dp(imu), step.shape[0], i32(step),
+                        _dp(pose), _dp(stamp), _dp(truth), C.byref(noise), sp, nb, int(stride), float(scn.spec.t_start),
+                        _dp(self.x), _dp(self.Ppk), _dp(self.aux), _dp(self.pend), i32(self.flags), i32(self.upds),
+                        *hist, *pf, int(bool(lazy)))
 
     def state(self):
         return self.x.copy()

@@ -119,7 +119,7 @@ template <typename T, bool BIAS, bool DIRECT>
 void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const double *imu, int64_t M,
            const int32_t *tag_step, const double *tag_pose, const double *tag_stamp, const uint8_t *tag_valid,
            double t_start, double *x, double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds,
-           const McArgs *mc = nullptr, const ExtArgs *ext = nullptr)
+           const McArgs *mc = nullptr, const ExtArgs *ext = nullptr, bool lazy = false)
 {
     constexpr int NS = BIAS ? 15 : 9;
     constexpr int NP = NS * (NS + 1) / 2;
@@ -197,7 +197,8 @@ void run_t(const qekf_params *p, int64_t N, int64_t k0, int64_t n_steps, const d
         int32_t mr_ints[MR_SCRATCH_INTS > SR_SCRATCH_INTS ? MR_SCRATCH_INTS : SR_SCRATCH_INTS];
 #define RUN_(S, F)                                                         \
         do {                                                               \
-            if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P, mr_ints, 1); \
+            if (mr && S && lazy) run_filter_mrs<T, BIAS, DIRECT, F>(a, i, P, mr_ints, 1); \
+            else if (mr) run_filter_mr<T, BIAS, DIRECT, S, F>(a, i, P, mr_ints, 1); \
             else run_filter<T, BIAS, DIRECT, S, F>(a, i, P, mr_ints, 1);   \
         } while (0)
         if (synth && pf) RUN_(true, true);
@@ -351,6 +352,32 @@ void hc_run_mc(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_
     ns.edge_loss = n->edge_loss; ns.range_ref = n->range_ref; ns.range_exp_p = n->range_exp_pos; ns.range_exp_th = n->range_exp_ang;
     McArgs mc = { &ns, truth, stats_acc, n_bins, stride };
 #define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu_clean, M, tag_step, tag_pose_clean, tag_stamp, nullptr, t_start, x, Ppk, aux, pend, flags, upds, &mc)
+    HC_DISPATCH(prec, p, C_);
+#undef C_
+}
+
+// Monte-Carlo replay with delayed fusion (and optional per-filter overrides).  lazy != 0: the loop that re-synthesises the
+// history inputs instead of keeping them in the ring (run_filter_mrs); the caller guarantees that the entries after
+// the checkpoints came from Monte-Carlo launches of the same noise model and scenario.
+void hc_run_mc_ext(const qekf_params *p, int prec, int64_t N, int64_t k0, int64_t n_steps, const double *imu_clean, int64_t M,
+                   const int32_t *tag_step, const double *tag_pose_clean, const double *tag_stamp, const double *truth,
+                   const qekf_noise_spec *n, double *stats_acc, int32_t n_bins, int32_t stride, double t_start, double *x,
+                   double *Ppk, double *aux, double *pend, int32_t *flags, int32_t *upds, double *xc, double *Pc, double *ring,
+                   int32_t *nh, int32_t *hpos, int32_t *hlen, int32_t ring_len, int32_t dmax, const double *pf_q,
+                   const double *pf_r, const double *pf_rvcv, const double *pf_qvc, const double *pf_delay, int lazy)
+{
+    NoiseSpec ns;
+    std::memset(&ns, 0, sizeof ns);
+    ns.seed = n->seed; ns.gid0 = n->first_global_id;
+    ns.sig_a = (float)n->sigma_accel; ns.sig_w = (float)n->sigma_gyro;
+    ns.sig_ba = (float)n->sigma_bias_accel; ns.sig_bw = (float)n->sigma_bias_gyro;
+    ns.sig_p = (float)n->sigma_tag_pos; ns.sig_th = (float)n->sigma_tag_ang;
+    ns.drop_k0 = n->dropout_k0; ns.drop_k1 = n->dropout_k1;
+    ns.rdrop_len = n->rand_dropout_len; ns.rdrop_lo = n->rand_dropout_lo; ns.rdrop_hi = n->rand_dropout_hi;
+    ns.edge_loss = n->edge_loss; ns.range_ref = n->range_ref; ns.range_exp_p = n->range_exp_pos; ns.range_exp_th = n->range_exp_ang;
+    McArgs mc = { &ns, truth, stats_acc, n_bins, stride };
+    ExtArgs e = { xc, Pc, ring, nh, hpos, hlen, ring_len, dmax, { pf_q, pf_r, pf_rvcv, pf_qvc, pf_delay } };
+#define C_(T, B, D) run_t<T, B, D>(p, N, k0, n_steps, imu_clean, M, tag_step, tag_pose_clean, tag_stamp, nullptr, t_start, x, Ppk, aux, pend, flags, upds, &mc, &e, lazy != 0)
     HC_DISPATCH(prec, p, C_);
 #undef C_
 }

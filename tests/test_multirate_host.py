@@ -110,3 +110,45 @@ def test_per_filter_parameter_sweep_matches_oracle(multirate, dynamic, direct):
         compare(hb, ob)
     # the sweep really produced different filters
     assert norm_rel(ob.cov()[:, :, 0], ob.cov()[:, :, 1]) > 1e-2
+
+
+@pytest.mark.parametrize("dynamic,est_bias,direct,sweep", [(0, 1, 1, 0), (1, 1, 1, 0), (1, 0, 0, 0), (1, 1, 1, 1)])
+def test_monte_carlo_delayed_fusion_without_ring_matches_ring_and_oracle(dynamic, est_bias, direct, sweep):
+    """The Monte-Carlo delayed-fusion loop that re-synthesises the history inputs and jumps from decision point to
+    decision point (run_filter_mrs, the product code instantiated for the host) against (i) the ring-based loop, bit
+    for bit, including the on-chip statistics, over chunked launches, and (ii) the dense oracle -- which keeps the
+    reference's x_hist / u_hist / P_hist vectors (relative_pose_EKF.cpp:196-264) -- replaying the dumped realisation."""
+    from quadrotor_landing_b200 import _native as nat
+    p = rotors_params(nat.default_params(), multirate=True, dynamic_delay=bool(dynamic), est_bias=est_bias, direct=direct)
+    scn = delayed_scenario(p, 0.042 if dynamic else 0.030, seconds=6.0)
+    noise = nat.default_noise()
+    noise.seed = 99
+    noise.first_global_id = 5_000_000_000
+    noise.dropout_k0, noise.dropout_k1 = 400, 520
+    noise.rand_dropout_len, noise.rand_dropout_lo, noise.rand_dropout_hi = 120, 100, 900
+    N, stride = 6, 200
+    nb = scn.T // stride
+    runs = []
+    for lazy in (False, True):
+        hb = hc.HostBatch(p, N)
+        if sweep:
+            for field, v in sweep_values(np.random.default_rng(4), p, N, True).items():
+                hb.set_filter_params(field, v)
+        acc = np.zeros((32, nb, 20))
+        for k0, n in ((0, 431), (431, 3), (434, scn.T - 434)):
+            hb.run_mc(scn, noise, k0, n, acc, stride, lazy=lazy)
+        runs.append((hb, acc.sum(axis=0)))
+    (ring, ring_stats), (lazy_b, lazy_stats) = runs
+    assert np.array_equal(ring.state(), lazy_b.state()) and np.array_equal(ring.cov(), lazy_b.cov())
+    assert np.array_equal(ring.aux, lazy_b.aux) and np.array_equal(ring.flags, lazy_b.flags) and np.array_equal(ring.upds, lazy_b.upds)
+    assert np.array_equal(ring.history_length(), lazy_b.history_length())
+    assert np.array_equal(ring_stats[:, 16:19], lazy_stats[:, 16:19]) and np.allclose(ring_stats, lazy_stats, rtol=1e-12, atol=0)
+    assert ring_stats[:, 16].sum() > 0
+    st = hc.synthesize(scn, noise, 0, N, params=p)
+    ob = orc.Batch(orc.params_from(p), N)
+    if sweep:
+        for field, v in sweep_values(np.random.default_rng(4), p, N, True).items():
+            ob.set_filter_params(field, v)
+    ob.run(0, scn.T, st["imu"], st["tag_step"], st["tag_pose"], st["tag_stamp"], st["tag_valid"])
+    compare(lazy_b, ob)
+    assert ob.counts()[1] > 50 * N
