@@ -223,7 +223,7 @@ int qekf_correction_step(qekf_handle *h, const double *tag_pose);
 /* ---- Monte-Carlo replay: one clean scenario shared by all filters, per-filter noise generated in-kernel ----
  * (no reference equivalent: the reference runs one filter on live sensors).  The noise realisation of a
  * filter depends only on (seed, global filter id, tick / arrival index): Philox4x32-10 keyed by the seed
- * with counter (index, stream, id), Box-Muller normals.  IMU: u = clean + bias_i + sigma n.  Tag, in the
+ * with counter (index, stream, id), one block = six 21-bit uniforms = three Box-Muller pairs.  IMU: u = clean + bias_i + sigma n.  Tag, in the
  * camera frame like the filter's R_k = N R N^T (src/relative_pose_EKF.cpp:462-472): r_c += sigma_p n,
  * q_ct <- exp(sigma_th n) (x) q_ct.  Dropouts: arrivals with dropout_k0 <= tag_step < dropout_k1 are lost
  * for every filter, plus rand_dropout_len ticks starting at a per-filter uniform tick in [lo, hi).

@@ -31,24 +31,35 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def uniforms21x6(w):
+    """Six 21-bit integers from the 128 bits of one Philox block (w: four uint32 arrays)."""
+    w0, w1, w2, w3 = (x.astype(np.uint32) for x in w)
+    u32 = np.uint32
+    return [w0 & u32(0x1FFFFF),
+            (w0 >> u32(21)) | ((w1 & u32(0x3FF)) << u32(11)),
+            (w1 >> u32(10)) & u32(0x1FFFFF),
+            (w1 >> u32(31)) | ((w2 & u32(0xFFFFF)) << u32(1)),
+            (w2 >> u32(20)) | ((w3 & u32(0x1FF)) << u32(12)),
+            (w3 >> u32(9)) & u32(0x1FFFFF)]
+
+
 def box_muller(a, b):
-    u1 = ((a >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
-    u2 = ((b >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+    u1 = (a.astype(np.float64) + 0.5) / 2097152.0
+    u2 = (b.astype(np.float64) + 0.5) / 2097152.0
     r = np.sqrt(-2.0 * np.log(u1))
     return r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)
 
 
 def normals6(seed, gid, stream, index):
-    """gid, index broadcastable integer arrays -> array [..., 6] of standard normals."""
+    """gid, index broadcastable integer arrays -> array [..., 6] of standard normals (one Philox block each)."""
     gid = np.asarray(gid, dtype=np.uint64)
     g0, g1 = (gid & MASK).astype(np.uint32), (gid >> np.uint64(32)).astype(np.uint32)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     idx = np.asarray(index, dtype=np.uint32)
-    w0 = philox4x32_10(idx, np.uint32(stream), g0, g1, k0, k1)
-    w1 = philox4x32_10(idx, np.uint32(stream + 1), g0, g1, k0, k1)
-    z0, z1 = box_muller(w0[0], w0[1])
-    z2, z3 = box_muller(w0[2], w0[3])
-    z4, z5 = box_muller(w1[0], w1[1])
+    u = uniforms21x6(philox4x32_10(idx, np.uint32(stream), g0, g1, k0, k1))
+    z0, z1 = box_muller(u[0], u[1])
+    z2, z3 = box_muller(u[2], u[3])
+    z4, z5 = box_muller(u[4], u[5])
     return np.stack([z0, z1, z2, z3, z4, z5], axis=-1)
 
 

@@ -990,7 +990,7 @@ template <typename T, int N> struct PNull {
 };
 
 // Roles 1 and 2 draw the noisy IMU sample of tick k -- the realisation synth_imu draws -- into half `uw` of the
-// exchange: role 1 components 0..3 (first Philox call, two Box-Muller pairs), role 2 components 4, 5 (second call).
+// exchange: role 1 components 0..3 (two Box-Muller pairs), role 2 components 4, 5.
 template <class PL, typename T = typename PL::real>
 QEKF_FN void synth_imu_role(const NoiseSpec &ns, int64_t gid, int64_t k, const double *clean6, const double bias[4], PL &P, int uw)
 {
@@ -999,19 +999,20 @@ QEKF_FN void synth_imu_role(const NoiseSpec &ns, int64_t gid, int64_t k, const d
     const uint32_t k0 = (uint32_t)ns.seed, k1 = (uint32_t)(ns.seed >> 32);
     const uint32_t g0 = (uint32_t)(uint64_t)gid, g1 = (uint32_t)((uint64_t)gid >> 32);
     const SPtr<T> u = P.sh + uw * S;
+    uint32_t uu[6];
+    philox4x32_10((uint32_t)k, STREAM_IMU, g0, g1, k0, k1, w);      // (one block; each role turns its share into normals)
+    uniforms21x6(w, uu);
     if (P.c == 1) {
-        philox4x32_10((uint32_t)k, STREAM_IMU, g0, g1, k0, k1, w);
         float z0, z1, z2, z3;
-        box_muller(w[0], w[1], z0, z1);
-        box_muller(w[2], w[3], z2, z3);
+        box_muller(uu[0], uu[1], z0, z1);
+        box_muller(uu[2], uu[3], z2, z3);
         sm_st(u + 0 * S, (T)(clean6[0] + bias[0] + (double)ns.sig_a * (double)z0));
         sm_st(u + 1 * S, (T)(clean6[1] + bias[1] + (double)ns.sig_a * (double)z1));
         sm_st(u + 2 * S, (T)(clean6[2] + bias[2] + (double)ns.sig_a * (double)z2));
         sm_st(u + 3 * S, (T)(clean6[3] + bias[3] + (double)ns.sig_w * (double)z3));
     } else {
-        philox4x32_10((uint32_t)k, STREAM_IMU + 1u, g0, g1, k0, k1, w);
         float z4, z5;
-        box_muller(w[0], w[1], z4, z5);
+        box_muller(uu[4], uu[5], z4, z5);
         sm_st(u + 4 * S, (T)(clean6[4] + bias[0] + (double)ns.sig_w * (double)z4));
         sm_st(u + 5 * S, (T)(clean6[5] + bias[1] + (double)ns.sig_w * (double)z5));
     }

@@ -4,8 +4,8 @@
 //
 // Noise: Philox4x32-10, key = 64-bit seed, counter = (index, stream tag, global filter id lo, hi), so a
 // realisation depends only on (seed, global filter id, tick/arrival index) -- never on the launch
-// geometry, the time chunking or the number of GPUs.  Normals by Box-Muller in FP32 (the FP32/SFU pipes
-// are idle while the FP64 pipe does the filter arithmetic), widened to the filter's real type.
+// geometry, the time chunking or the number of GPUs.  One block gives six 21-bit uniforms; normals by Box-Muller in
+// FP32 (the FP32/SFU pipes are idle while the FP64 pipe does the filter arithmetic), widened to the filter's real type.
 //
 // Measurement noise is applied in the camera frame, which is where the filter's R_k = N R N^T places it
 // (relative_pose_EKF.cpp:462-472):  r_c += n_p,  q_ct <- exp(n_th) (x) q_ct.
@@ -53,11 +53,23 @@ QEKF_FN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// two standard normals from two 32-bit words (Box-Muller, FP32)
+// six 21-bit integers from the 128 bits of one Philox block (126 of them used)
+QEKF_FN void uniforms21x6(const uint32_t w[4], uint32_t u[6])
+{
+    u[0] = w[0] & 0x1FFFFFu;
+    u[1] = (w[0] >> 21) | ((w[1] & 0x3FFu) << 11);
+    u[2] = (w[1] >> 10) & 0x1FFFFFu;
+    u[3] = (w[1] >> 31) | ((w[2] & 0xFFFFFu) << 1);
+    u[4] = (w[2] >> 20) | ((w[3] & 0x1FFu) << 12);
+    u[5] = (w[3] >> 9) & 0x1FFFFFu;
+}
+
+// two standard normals from two 21-bit integers (Box-Muller, FP32): u = (a + 1/2) / 2^21 lies strictly inside (0, 1)
+// and is exact in float; the largest |z| is sqrt(-2 ln 2^-22) = 5.5
 QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
 {
-    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), never 0
-    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u1 = ((float)a + 0.5f) * (1.0f / 2097152.0f);
+    const float u2 = ((float)b + 0.5f) * (1.0f / 2097152.0f);
     float s, c;
 #ifdef __CUDA_ARCH__
     // r = sqrt(-2 ln u1) from the SFU (lg2.approx, sqrt.approx) instead of logf + sqrtf (41 -> ~15 instructions per pair,
@@ -69,15 +81,12 @@ QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
     const float nl = (t < 0.0625f) ? ser : -0.69314718f * __log2f(u1);
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(2.0f * nl));
-#else
-    const float r = sqrtf(-2.0f * logf(u1));
-#endif
-#ifdef __CUDA_ARCH__
     // the SFU's sin / cos (absolute error < 7e-7 on [0, 2 pi): a relative 7e-7 of a noise sample) instead of sincospif's
     // range reduction and two polynomials: 6 instructions per pair instead of 35, on the per-tick path of every filter
     s = __sinf(6.2831853071795865f * u2);
     c = __cosf(6.2831853071795865f * u2);
 #else
+    const float r = sqrtf(-2.0f * logf(u1));
     s = (float)::sin(6.283185307179586 * (double)u2);
     c = (float)::cos(6.283185307179586 * (double)u2);
 #endif
@@ -85,17 +94,18 @@ QEKF_FN void box_muller(uint32_t a, uint32_t b, float &z0, float &z1)
     z1 = r * s;
 }
 
-// six standard normals for (seed, global filter id, stream, index)
+// six standard normals for (seed, global filter id, stream, index): ONE Philox block (two until late in round 2: the
+// second block was 7 % of a tick's instructions for two of its four words)
 QEKF_FN void normals6(uint64_t seed, int64_t gid, uint32_t stream, uint32_t index, float z[6])
 {
-    uint32_t w0[4], w1[4];
+    uint32_t w[4], u[6];
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t g0 = (uint32_t)(uint64_t)gid, g1 = (uint32_t)((uint64_t)gid >> 32);
-    philox4x32_10(index, stream, g0, g1, k0, k1, w0);
-    philox4x32_10(index, stream + 1u, g0, g1, k0, k1, w1);
-    box_muller(w0[0], w0[1], z[0], z[1]);
-    box_muller(w0[2], w0[3], z[2], z[3]);
-    box_muller(w1[0], w1[1], z[4], z[5]);
+    philox4x32_10(index, stream, g0, g1, k0, k1, w);
+    uniforms21x6(w, u);
+    box_muller(u[0], u[1], z[0], z[1]);
+    box_muller(u[2], u[3], z[2], z[3]);
+    box_muller(u[4], u[5], z[4], z[5]);
 }
 QEKF_FN void normals6(const NoiseSpec &ns, int64_t gid, uint32_t stream, uint32_t index, float z[6])
 {
