@@ -224,7 +224,7 @@ template <typename T, bool SYNTH> struct Inputs {
 // tick), so that the 20 sums can be reduced over the warp with shuffles and leave as ONE atomic per warp and
 // statistic instead of one per lane.  Deliberately NOT inlined on the device: it runs once per `stride` ticks
 // and must not take part in the register allocation of the hot loop.
-// SAVE = false: P is a scratch copy that may be destroyed (the cooperative mapping, ekf_coop.cuh).
+// (SAVE is a leftover of the in-place NEES factorisation, which had to park P in HBM; the covariance is only read now.)
 template <typename T, bool BIAS, class PS, bool SAVE = true>
 QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nominal<T> s, PS P, const double *bias,
                             bool valid)
@@ -234,12 +234,6 @@ QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nom
     // by value: this function is reached through a generic reference to the kernel parameters, and every store
     // below would otherwise force the compiler to reload these fields (it cannot rule out aliasing)
     const StatsView sv = a.stats;
-    const int64_t ld = a.st.ld;
-#ifdef __CUDA_ARCH__
-    T *const __restrict__ gp = sv.save ? static_cast<T *>(sv.save) + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) : a.st.P + i;
-#else
-    T *const __restrict__ gp = a.st.P + i;
-#endif
     int32_t bin = (int32_t)((k + 1) / sv.stride - 1);
     if (bin < 0 || bin >= sv.n_bins) valid = false;
     double sum[STAT_DIM];
@@ -260,18 +254,9 @@ QEKF_COLD void stats_sample(const RunArgs<T> &a, int64_t i, int64_t k, const Nom
 #pragma unroll
             for (int c = 0; c < 3; ++c) { e[9 + c] = (T)bias[c] - s.ab[c]; e[12 + c] = (T)bias[3 + c] - s.wb[c]; }
         }
-        // save P, factor in place, restore
-        // (the restore is unrolled deep: with 7 warps per SM nothing else hides its DRAM round trips)
-        if (SAVE) {
-#pragma unroll 8
-            for (int el = 0; el < NP; ++el) gp[el * ld] = P.el(el);
-        }
+        // (the covariance is only read: see nees_readonly)
         T nees;
-        bool ok = nees_inplace<T>(P, e, nees);
-        if (SAVE) {
-#pragma unroll 40
-            for (int el = 0; el < NP; ++el) P.el(el) = gp[el * ld];
-        }
+        bool ok = nees_readonly<T>(P, e, nees);
         bool finite = true;
 #pragma unroll
         for (int c = 0; c < N; ++c) { finite = finite && (M<T>::abs_(e[c]) < T(1e30)); }
