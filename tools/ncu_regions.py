@@ -11,18 +11,14 @@ div = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 def region(f, l):
     # (line ranges of the sources at the end of round 2)
     if f == "ekf_core.cuh":
-        for hi, name in ((59, "core:scalar wrappers (fma/sqrt..)"), (329, "core:P ld/st + 3x3 helpers"), (491, "core:quat/attitude"),
-                         (529, "core:init_state"), (594, "core:pred_nominal"), (770, "core:pred_cov"), (836, "core:sym6inv"),
-                         (942, "core:corr_front"), (1151, "core:correction")):
+        for hi, name in ((59, "core:scalar wrappers (fma/sqrt..)"), (341, "core:P ld/st + 3x3 helpers"), (503, "core:quat/attitude"), (541, "core:init_state"), (606, "core:pred_nominal"), (782, "core:pred_cov"), (848, "core:sym6inv"), (954, "core:corr_front"), (1163, "core:correction")):
             if l <= hi:
                 return name
         return "core:gate"
     if f == "ekf_synth.cuh":
-        return "synth:nees" if l >= 230 else "synth:noise"
+        return "synth:nees" if l >= 243 else "synth:noise"
     if f == "ekf_kernels.cuh":
-        for hi, name in ((229, "k:inputs"), (315, "k:stats_sample"), (358, "k:load/store filter"), (374, "k:correction_call"),
-                         (459, "k:votes"), (495, "k:SmemInt"), (705, "k:run_filter (single rate)"), (775, "k:checkpoint/advance_call"),
-                         (1019, "k:run_filter_mr (ring)"), (1049, "k:advance_synth_call"), (1298, "k:run_filter_mrs (no ring)")):
+        for hi, name in ((229, "k:inputs"), (300, "k:stats_sample"), (343, "k:load/store filter"), (359, "k:correction_call"), (444, "k:votes"), (480, "k:SmemInt"), (690, "k:run_filter (single rate)"), (760, "k:checkpoint/advance_call"), (1004, "k:run_filter_mr (ring)"), (1034, "k:advance_synth_call"), (1283, "k:run_filter_mrs (no ring)")):
             if l <= hi:
                 return name
         return "k:kernels"
