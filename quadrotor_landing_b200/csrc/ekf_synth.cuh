@@ -246,9 +246,6 @@ struct StatsView {
     int32_t n_bins;
     int32_t stride;               // sample after tick k when (k+1) % stride == 0
     double chi2_lo, chi2_hi;
-    void *save;                   // [NP][ld] of the filter's real type, indexed by thread slot: where a sample parks the
-                                  // covariance while it factors it in place (nullptr: the filter's own HBM home, which is
-                                  // only coalesced when slot j advances filter j)
 };
 
 // Cholesky U^T U of a packed upper triangle held in registers (sym_idx<NN>), in place, with one right-hand side

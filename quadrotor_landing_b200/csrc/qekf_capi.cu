@@ -317,7 +317,6 @@ int run_typed(qekf_handle *h, const StreamView &in, int64_t k0, int64_t n_steps,
         a.st.gid_perm = h->in_slot_order ? h->d_perm : nullptr;
         a.st.hist_synth = h->lazy_now ? 1 : 0;
         if (h->stats_acc && truth && h->stats_stride > 0) {
-            a.stats.save = nullptr;
             a.stats.acc = h->stats_acc; a.stats.truth = truth;
             a.stats.n_bins = h->stats_bins; a.stats.stride = h->stats_stride;
             // two-sided 95% chi-square interval for n degrees of freedom
